@@ -1,0 +1,223 @@
+"""Generate golden vectors from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py            # needs /root/reference
+
+The reference has no tests or fixtures of its own, so parity is pinned on
+outputs of its own modules executed here on CPU with seeded synthetic weights in the real
+key layout.  The `.npz` files written next to this script are committed; nothing on the GPU
+box reads /root/reference.  The only shim applied is `.cuda()` -> no-op (the reference calls
+bare `.cuda()` at matcher.py:48,58,210,...), nothing else is patched.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from simplesfm_b200 import synthetic as S  # noqa: E402
+
+torch.nn.Module.cuda = lambda self, *a, **k: self
+torch.Tensor.cuda = lambda self, *a, **k: self
+torch.cuda.empty_cache = lambda: None
+
+from simple_sfm.models import superpoint as RSP  # noqa: E402
+from simple_sfm.models import superglue as RSG  # noqa: E402
+from simple_sfm.matchers.matcher import Matcher, Frame  # noqa: E402
+from simple_sfm.matchers.simple_matcher import SimpleMatcher  # noqa: E402
+
+torch.set_num_threads(8)
+TMP = tempfile.mkdtemp()
+
+
+def npz(name, **arrs):
+    out = {}
+    for k, v in arrs.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}.npz  {os.path.getsize(path) / 1024:.0f} KB")
+
+
+def golden_superpoint():
+    wpath = S.save_state_dict(S.superpoint_state_dict(0), os.path.join(TMP, "sp.pth"))
+    # --- small image, every stage -------------------------------------------------------
+    img = S.textured_image(3, 120, 160)
+    mask = torch.ones(1, 1, 120, 160, dtype=torch.bool)
+    mask[:, :, 30:70, 50:120] = False
+    for tag, mk, use_mask in (("all", -1, False), ("top200", 200, False), ("masked", -1, True)):
+        m = RSP.SuperPoint(wpath, nms_radius=4, keypoint_threshold=0.005, max_keypoints=mk)
+        stages = {}
+        with torch.no_grad():
+            x = img
+            for a, b, pool in (("conv1a", "conv1b", True), ("conv2a", "conv2b", True),
+                               ("conv3a", "conv3b", True), ("conv4a", "conv4b", False)):
+                x = m.relu(getattr(m, b)(m.relu(getattr(m, a)(x))))
+                if pool:
+                    x = m.pool(x)
+            stages["feat"] = x
+            logits = m.convPb(m.relu(m.convPa(x)))
+            stages["logits"] = logits
+            sc = torch.nn.functional.softmax(logits, 1)[:, :-1]
+            b_, _, h, w = sc.shape
+            sc = sc.permute(0, 2, 3, 1).reshape(b_, h, w, 8, 8).permute(0, 1, 3, 2, 4).reshape(b_, h * 8, w * 8)
+            stages["score_map"] = sc
+            stages["nms"] = RSP.simple_nms(sc, 4)
+            stages["dmap"] = torch.nn.functional.normalize(m.convDb(m.relu(m.convDa(x))), p=2, dim=1)
+            data = {"image": img}
+            if use_mask:
+                data["mask"] = mask
+            out = m(data)
+        if tag == "all":
+            npz("sp_small_stages", image=img, **stages)
+        npz(f"sp_small_{tag}", image=img, mask=mask if use_mask else np.zeros(0),
+            keypoints=out["keypoints"], scores=out["scores"], descriptors=out["descriptors"])
+    # --- full 480x640, final outputs (descriptors of the 128 best only) ------------------
+    img = S.textured_image(1, 480, 640)
+    m = RSP.SuperPoint(wpath, nms_radius=4, keypoint_threshold=0.005, max_keypoints=1024)
+    with torch.no_grad():
+        out = m({"image": img})
+    npz("sp_480x640_top1024", seed=1, keypoints=out["keypoints"], scores=out["scores"],
+        descriptors_first128=out["descriptors"][:, :128])
+    # --- free functions ------------------------------------------------------------------
+    g = torch.Generator().manual_seed(5)
+    smap = torch.rand(2, 64, 96, generator=g)
+    smap[0, 10:30, 10:30] = 0.7                       # plateau: every interior pixel survives
+    smap[1, 5, 5] = 2.0
+    npz("sp_functions",
+        nms_in=smap, nms_r4=RSP.simple_nms(smap, 4), nms_r2=RSP.simple_nms(smap, 2), nms_r0=RSP.simple_nms(smap, 0),
+        samp_kpts=(kp := torch.stack([torch.randint(0, 160, (50,), generator=g),
+                                     torch.randint(0, 120, (50,), generator=g)], 1).float()),
+        samp_dmap=(dm := torch.nn.functional.normalize(torch.randn(1, 256, 15, 20, generator=g), dim=1)),
+        samp_out=RSP.sample_descriptors(kp.clone()[None], dm, 8)[0],
+        torch_version=np.array(torch.__version__))
+
+
+def sg_inputs(B, K0, K1, seed):
+    fr = S.feature_scene(2 * B, max(K0, K1), seed=seed)
+    return {"descriptors0": torch.stack([fr[i][0][:, :K0] for i in range(B)]),
+            "descriptors1": torch.stack([fr[B + i][0][:, :K1] for i in range(B)]),
+            "keypoints0": torch.stack([fr[i][1][:K0] for i in range(B)]),
+            "keypoints1": torch.stack([fr[B + i][1][:K1] for i in range(B)]),
+            "scores0": torch.stack([fr[i][2][:K0] for i in range(B)]),
+            "scores1": torch.stack([fr[B + i][2][:K1] for i in range(B)]),
+            "image0": torch.zeros(B, 1, 480, 640), "image1": torch.zeros(B, 1, 480, 640)}
+
+
+def golden_superglue():
+    wpath = S.save_state_dict(S.superglue_state_dict(0, "indoor"), os.path.join(TMP, "sg.pth"))
+    data = sg_inputs(2, 96, 80, seed=11)
+    for mode in ("train", "eval"):
+        for iters in (20, 100):
+            m = RSG.SuperGlue(wpath, sinkhorn_iterations=iters, match_threshold=0.2)
+            if mode == "eval":
+                m.eval()
+            keep = {}
+            hooks = []
+            for li in (0, 1, 17):
+                hooks.append(m.gnn.layers[li].register_forward_hook(
+                    lambda mod, inp, out, li=li: keep.setdefault(f"delta_l{li}", []).append(out.clone())))
+            hooks.append(m.kenc.register_forward_hook(
+                lambda mod, inp, out: keep.setdefault("kenc", []).append(out.clone())))
+            hooks.append(m.final_proj.register_forward_hook(
+                lambda mod, inp, out: keep.setdefault("mdesc", []).append(out.clone())))
+            with torch.no_grad():
+                out = m(data)
+                md0, md1 = keep["mdesc"]
+                scores = torch.einsum("bdn,bdm->bnm", md0, md1) / 16.0
+                Z = RSG.log_optimal_transport(scores, m.bin_score, iters)
+            extra = {}
+            for k, v in keep.items():
+                extra[k + "_0"], extra[k + "_1"] = v[0], v[1]
+            if iters == 100:
+                extra = {}   # per-layer tensors are identical; keep the file small
+            npz(f"sg_b2_{mode}_it{iters}", **{k: v for k, v in data.items() if "image" not in k},
+                image_hw=np.array([480, 640]), scores=scores, Z=Z, **extra, **out)
+    # empty side
+    m = RSG.SuperGlue(wpath)
+    d = sg_inputs(1, 8, 8, seed=3)
+    d["keypoints1"] = d["keypoints1"][:, :0]
+    d["descriptors1"] = d["descriptors1"][:, :, :0]
+    d["scores1"] = d["scores1"][:, :0]
+    with torch.no_grad():
+        out = m(d)
+    npz("sg_empty_side", **{k: v for k, v in out.items()},
+        dtypes=np.array([str(out["matches0"].dtype), str(out["matching_scores0"].dtype)]))
+    # free functions
+    g = torch.Generator().manual_seed(9)
+    sc = torch.randn(3, 37, 29, generator=g) * 3
+    q = torch.randn(2, 64, 4, 33, generator=g)
+    k = torch.randn(2, 64, 4, 21, generator=g)
+    v = torch.randn(2, 64, 4, 21, generator=g)
+    kp = torch.rand(2, 17, 2, generator=g) * 600
+    npz("sg_functions",
+        ot_scores=sc, ot_alpha=np.float32(1.0),
+        ot_it20=RSG.log_optimal_transport(sc, torch.tensor(1.0), 20),
+        ot_it100=RSG.log_optimal_transport(sc, torch.tensor(1.0), 100),
+        ot_alpha2_it5=RSG.log_optimal_transport(sc, torch.tensor(2.5), 5),
+        att_q=q, att_k=k, att_v=v, att_out=RSG.attention(q, k, v)[0],
+        nk_in=kp, nk_out=RSG.normalize_keypoints(kp, (2, 1, 480, 640)),
+        nk_out_tall=RSG.normalize_keypoints(kp, (2, 1, 640, 480)),
+        arange=RSG.arange_like(torch.zeros(2, 7), 1))
+
+
+def golden_matcher():
+    sp = S.save_state_dict(S.superpoint_state_dict(0), os.path.join(TMP, "sp.pth"))
+    sg = S.save_state_dict(S.superglue_state_dict(1, "outdoor"), os.path.join(TMP, "sgo.pth"))
+    fr = S.feature_scene(4, 160, seed=21)
+    counts = [160, 131, 160, 97]                     # ragged: exercises chunk-min truncation
+    frames = [Frame(fr[i][0][:, :c], fr[i][1][:c], fr[i][2][:c], torch.zeros(1, 480, 640))
+              for i, c in enumerate(counts)]
+    names = {i + 1: f"img_{i:03d}.png" for i in range(4)}
+    save = {}
+    for i, f in enumerate(frames):
+        save[f"desc_{i}"], save[f"kpts_{i}"], save[f"scores_{i}"] = f.descriptors, f.keypoints_poses, f.scores
+    for batch in (4, 1):
+        m = Matcher(sp, 4, 0.005, matcher_type="super_glue", super_glue_weights_path=sg,
+                    match_threshold=0.2, sinkhorn_iterations=20, super_glue_batch=batch)
+        _, table, _ = m.match_frames(frames, names, lambda p: True)
+        for (a, b), t in table.items():
+            save[f"sg_b{batch}_{int(a)}_{int(b)}"] = t
+        save[f"sg_b{batch}_keytype"] = np.array(str(type(next(iter(table.keys()))[0])))
+    m = Matcher(sp, 4, 0.005, matcher_type="super_glue", super_glue_weights_path=sg,
+                match_threshold=0.2, sinkhorn_iterations=20, super_glue_batch=4)
+    _, table, _ = m.match_frames(frames, names, lambda p: abs(p[0] - p[1]) <= 2)
+    save["sg_filtered_keys"] = np.array(sorted((int(a), int(b)) for a, b in table.keys()))
+    m = Matcher(sp, 4, 0.005, matcher_type="simple", match_threshold=0.7)
+    _, table, _ = m.match_frames(frames, names, lambda p: True)
+    for (a, b), t in table.items():
+        save[f"simple_{int(a)}_{int(b)}"] = t
+    sm = SimpleMatcher(0.7)
+    save["simple_two_way_np"] = sm.match_two_way(frames[0].descriptors, frames[1].descriptors)
+    save["simple_two_way_cuda"] = sm.match_two_way_cuda(frames[0].descriptors, frames[1].descriptors)
+    npz("matcher_4frames", counts=np.array(counts), **save)
+    # full image -> frames -> tables through the reference Matcher's own extraction code path
+    imgs = [S.textured_image(40, 120, 160, shift=(0, 0)), S.textured_image(40, 120, 160, shift=(3, 5)),
+            S.textured_image(40, 120, 160, shift=(-4, 2))]
+    m = Matcher(sp, 4, 0.005, matcher_type="super_glue", super_glue_weights_path=sg,
+                match_threshold=0.2, sinkhorn_iterations=20, super_glue_batch=2)
+    frs = []
+    with torch.no_grad():
+        for im in imgs:
+            r = m.super_point_extractor({"image": im})
+            frs.append(Frame(r["descriptors"], r["keypoints"], r["scores"], im[0]))
+    _, table, _ = m.match_frames(frs, {1: "a", 2: "b", 3: "c"}, lambda p: True)
+    save = {f"image_{i}": im for i, im in enumerate(imgs)}
+    for i, f in enumerate(frs):
+        save[f"kpts_{i}"], save[f"scores_{i}"] = f.keypoints_poses, f.scores
+    for (a, b), t in table.items():
+        save[f"table_{int(a)}_{int(b)}"] = t
+    npz("matcher_images_e2e", **save)
+
+
+if __name__ == "__main__":
+    golden_superpoint()
+    golden_superglue()
+    golden_matcher()
