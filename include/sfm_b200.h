@@ -1,0 +1,145 @@
+/* libsfm_b200 -- C ABI of the B200-native SuperPoint -> SuperGlue matching path.
+ *
+ * The reference (palsol/SimpleSfm) has no FFI layer: its boundary for this path is the Python
+ * API of `simple_sfm.matchers` / `simple_sfm.models.{superpoint,superglue}`.  Each entry point
+ * below names the reference interface it replaces (paths relative to the reference root).  The
+ * host-side mirror of those Python classes lives in `simplesfm_b200/` and binds this header
+ * with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative SFM_ERR_* code; sfm_last_error() gives
+ *     a thread-local message.  No C++ exception crosses the boundary.
+ *   - all tensor arguments are DEVICE pointers unless the name ends in `_host`; the caller
+ *     (torch) owns inputs, outputs and workspaces.  The handle owns only the packed weights.
+ *   - every compute entry point is asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - there is no CPU fallback: without a CUDA device sfm_create fails.
+ */
+#ifndef SFM_B200_H_
+#define SFM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFM_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SFM_API __attribute__((visibility("default")))
+#else
+#define SFM_API
+#endif
+
+#define SFM_OK 0
+#define SFM_ERR_INVALID (-1)
+#define SFM_ERR_CUDA (-2)
+#define SFM_ERR_WORKSPACE (-3)
+#define SFM_ERR_STATE (-4)
+#define SFM_ERR_UNSUPPORTED (-5)
+
+/* BatchNorm1d behaviour inside SuperGlue's MLPs (superglue.py:56-57).  The reference never calls
+ * .eval(), so as run it uses batch statistics (SFM_BN_TRAIN, the default of the mirror). */
+#define SFM_BN_TRAIN 0
+#define SFM_BN_EVAL 1
+
+/* arithmetic of the contraction kernels */
+#define SFM_PREC_FP32 0 /* FFMA, reproduces the reference's fp32 results (bit-exact matches) */
+#define SFM_PREC_BF16 1 /* tcgen05 bf16 operands, fp32 accumulate (throughput mode)          */
+
+typedef struct sfm_ctx* sfm_handle_t;
+
+SFM_API int sfm_abi_version(void);
+SFM_API const char* sfm_last_error(void);
+
+/* one handle per GPU; holds packed weights only */
+SFM_API int sfm_create(int device, sfm_handle_t* out);
+SFM_API int sfm_destroy(sfm_handle_t h);
+
+/* ---- weights -------------------------------------------------------------------------------
+ * SuperPoint.__init__ -> load_state_dict (superpoint.py:101).  `packed_host`: the 12 convs in the
+ * order conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db, each as weight (Cout,Cin,kh,kw) then bias, f32,
+ * 1 300 865 floats in total. */
+SFM_API int sfm_load_superpoint(sfm_handle_t h, const float* packed_host, size_t n_floats);
+SFM_API size_t sfm_superpoint_packed_floats(void);
+
+/* SuperGlue.__init__ -> load_state_dict (superglue.py:233).  `packed_host` order:
+ *   bin_score; kenc.encoder.{0,3,6,9,12} as (weight, bias) each followed (except the last) by its
+ *   BatchNorm (weight, bias, running_mean, running_var); for L in 0..17: proj.0, proj.1, proj.2,
+ *   merge (weight, bias each), mlp.0 (weight, bias), mlp.1 BN (weight, bias, running_mean,
+ *   running_var), mlp.3 (weight, bias); final_proj (weight, bias).  Channel order as stored by the
+ *   reference (interleaved heads); the library re-orders internally. */
+SFM_API int sfm_load_superglue(sfm_handle_t h, const float* packed_host, size_t n_floats);
+SFM_API size_t sfm_superglue_packed_floats(void);
+
+/* ---- SuperPoint.forward (superpoint.py:109-171) ----------------------------------------------
+ * images [n,H,W] f32 in [0,1]; mask [n,H,W] u8 (0 = masked out) or NULL.  H, W multiples of 8.
+ * detect : encoder + detector head + softmax/shuffle + simple_nms + mask/threshold/border
+ *          compaction; cand_counts[n] = number of surviving candidates per image.
+ * describe: top-k (max_keypoints, -1 = all) + score-descending sort (ties: pixel index
+ *          ascending) + descriptor head + bilinear sampling + L2 normalise.
+ *          kpts_xy [n,kp_cap,2], scores [n,kp_cap], desc [n,256,kp_cap] (reference layout),
+ *          counts[n] = min(candidates, max_keypoints, kp_cap).
+ * Both use the same workspace, which must stay untouched between the two calls. */
+SFM_API size_t sfm_superpoint_workspace_bytes(int n_img, int H, int W, int precision);
+SFM_API int sfm_superpoint_detect(sfm_handle_t h, const float* images, int n_img, int H, int W, const uint8_t* mask,
+                          float keypoint_threshold, int nms_radius, int remove_borders, int precision,
+                          int* cand_counts, void* workspace, size_t workspace_bytes, void* stream);
+SFM_API int sfm_superpoint_describe(sfm_handle_t h, int n_img, int H, int W, int max_keypoints, int align_corners,
+                            int precision, int kp_cap, float* kpts_xy, float* scores, float* desc, int* counts,
+                            void* workspace, size_t workspace_bytes, void* stream);
+/* debug/parity taps into the detect workspace: which = 0 feat NHWC [n,H/8,W/8,128], 1 logits
+ * [n,H/8,W/8,65], 2 score map [n,H,W], 3 nms map [n,H,W], 4 raw descriptor map NHWC [n,H/8,W/8,256] */
+SFM_API int sfm_superpoint_tap(int n_img, int H, int W, int precision, int which, void* workspace, size_t workspace_bytes,
+                       float** out_ptr, size_t* out_floats);
+
+/* module-level functions of superpoint.py */
+SFM_API int sfm_simple_nms(const float* scores, float* out, int n_img, int H, int W, int nms_radius, void* stream); /* :9-24 */
+SFM_API int sfm_sample_descriptors(const float* dmap_nhwc, int n_img, int h, int w, const float* kpts_xy, const int* counts,
+                           int kp_cap, int align_corners, float* desc, void* stream); /* :42-54 (+ :159 normalise) */
+
+/* ---- SuperGlue.forward (superglue.py:235-290) ------------------------------------------------
+ * Per-image feature records: desc (n_img,256,ldk) f32, kpts (n_img,kcap,2), scores (n_img,kcap).
+ * A batch of B pairs is (idx0[b], idx1[b]) into those records (NULL = identity, i.e. the record
+ * arrays ARE the (B,256,K) batch tensors of the reference).  K0/K1: keypoints used per side (the
+ * caller applies the reference's chunk-minimum truncation, matcher.py:82-91).
+ * Outputs: matches0 (B,K0) i64, matches1 (B,K1) i64, matching_scores0/1 f32. */
+SFM_API size_t sfm_superglue_workspace_bytes(int B, int K0, int K1, int precision);
+SFM_API int sfm_superglue_forward(sfm_handle_t h,
+                          const float* desc0, const float* kpts0, const float* scores0, int ldk0, int kcap0,
+                          const int* idx0,
+                          const float* desc1, const float* kpts1, const float* scores1, int ldk1, int kcap1,
+                          const int* idx1,
+                          int B, int K0, int K1, int H0, int W0, int H1, int W1,
+                          int sinkhorn_iterations, float match_threshold, int bn_mode, int precision,
+                          int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
+                          void* workspace, size_t workspace_bytes, void* stream);
+/* parity taps into the forward workspace: which = 0 descriptors after kenc (token-major
+ * [B*K0 + B*K1, 256]), 1 after the GNN, 2 score matrix [B,K0,K1], 3 u [B,K0+1], 4 v [B,K1+1] */
+SFM_API int sfm_superglue_tap(int B, int K0, int K1, int precision, int which, void* workspace, size_t workspace_bytes,
+                      float** out_ptr, size_t* out_floats);
+
+/* log_optimal_transport (superglue.py:151-171): scores (B,N,M) -> Z (B,N+1,M+1) */
+SFM_API size_t sfm_sinkhorn_workspace_bytes(int B, int N, int M);
+SFM_API int sfm_log_optimal_transport(const float* scores, int B, int N, int M, float alpha, int iters, float* Z,
+                              void* workspace, size_t workspace_bytes, void* stream);
+/* Sinkhorn + mutual-NN + threshold without materialising Z (superglue.py:268-283; BASELINE config 5) */
+SFM_API int sfm_sinkhorn_match(const float* scores, int B, int N, int M, float alpha, int iters, float match_threshold,
+                       int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Matcher.__super_glue_matcher tail (matcher.py:103-109): per pair (L,2) uint32 rows
+ * [i, matches0[i]] for matches0[i] > -1, in ascending i.  tables (B,K0,2) u32, lengths (B) i32. */
+SFM_API int sfm_compact_matches(const int64_t* matches0, int B, int K0, uint32_t* tables, int* lengths, void* stream);
+
+/* SimpleMatcher.match_two_way(_cuda) (simple_matcher.py:66-114): desc (256,N) / (256,M) unit f32.
+ * out (3, min(N,M)) f32 rows [i, j, dist], count = L. */
+SFM_API size_t sfm_simple_match_workspace_bytes(int N, int M);
+SFM_API int sfm_simple_match(const float* desc1, int ld1, int N, const float* desc2, int ld2, int M, float nn_thresh,
+                     float* out, int out_ld, int* count, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFM_B200_H_ */

@@ -1,0 +1,447 @@
+// extern "C" surface of libsfm_b200 (declared in include/sfm_b200.h).
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/sfm_b200.h"
+#include "context.cuh"
+#include "gemm_f32.cuh"
+#include "sg_kernels.cuh"
+#include "sp_post.cuh"
+
+namespace sfm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return SFM_ERR_CUDA;
+}
+
+namespace {
+
+template <typename T>
+int upload(sfm_ctx* h, const std::vector<T>& host, T** dev) {
+  void* p = nullptr;
+  SFM_CUDA(cudaMalloc(&p, host.size() * sizeof(T) + 16));
+  h->allocs.push_back(p);
+  SFM_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *dev = (T*)p;
+  return SFM_OK;
+}
+
+int upload_bf16(sfm_ctx* h, const std::vector<float>& host, __nv_bfloat16** dev) {
+  std::vector<__nv_bfloat16> t(host.size());
+  for (size_t i = 0; i < host.size(); i++) t[i] = __float2bfloat16(host[i]);
+  return upload(h, t, dev);
+}
+
+constexpr int SP_DIMS[12][3] = {{1, 64, 3},    {64, 64, 3},   {64, 64, 3},   {64, 64, 3},
+                                {64, 128, 3},  {128, 128, 3}, {128, 128, 3}, {128, 128, 3},
+                                {128, 256, 3}, {256, 65, 1},  {128, 256, 3}, {256, 256, 1}};
+
+size_t sp_packed_floats() {
+  size_t n = 0;
+  for (auto& d : SP_DIMS) n += (size_t)d[1] * d[0] * d[2] * d[2] + d[1];
+  return n;
+}
+
+constexpr int KCH[6] = {3, 32, 64, 128, 256, 256};
+
+size_t sg_packed_floats() {
+  size_t n = 1;
+  for (int i = 0; i < 5; i++) {
+    n += (size_t)KCH[i + 1] * KCH[i] + KCH[i + 1];
+    if (i < 4) n += 4 * (size_t)KCH[i + 1];
+  }
+  size_t layer = 4 * (256 * 256 + 256) + (512 * 512 + 512) + 4 * 512 + (256 * 512 + 256);
+  n += 18 * layer;
+  n += 256 * 256 + 256;
+  return n;
+}
+
+struct Reader {
+  const float* p;
+  size_t left;
+  std::vector<float> take(size_t n) {
+    std::vector<float> v(p, p + n);
+    p += n;
+    left -= n;
+    return v;
+  }
+};
+
+void fold_bn(const std::vector<float>& W, const std::vector<float>& b, const std::vector<float>& g,
+             const std::vector<float>& be, const std::vector<float>& rm, const std::vector<float>& rv, int cout,
+             int cin, std::vector<float>& Wf, std::vector<float>& bf) {
+  Wf.resize(W.size());
+  bf.resize(cout);
+  for (int o = 0; o < cout; o++) {
+    float s = g[o] / sqrtf(rv[o] + 1e-5f);
+    for (int i = 0; i < cin; i++) Wf[(size_t)o * cin + i] = W[(size_t)o * cin + i] * s;
+    bf[o] = (b[o] - rm[o]) * s + be[o];
+  }
+}
+
+}  // namespace
+}  // namespace sfm
+
+using namespace sfm;
+
+extern "C" {
+
+int sfm_abi_version(void) { return SFM_ABI_VERSION; }
+const char* sfm_last_error(void) { return sfm::g_err; }
+size_t sfm_superpoint_packed_floats(void) { return sp_packed_floats(); }
+size_t sfm_superglue_packed_floats(void) { return sg_packed_floats(); }
+
+int sfm_create(int device, sfm_handle_t* out) {
+  SFM_REQUIRE(out != nullptr, "sfm_create: out is NULL");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("sfm_create: no CUDA device available (%s); this library has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return SFM_ERR_CUDA;
+  }
+  SFM_REQUIRE(device >= 0 && device < count, "sfm_create: device %d out of range [0,%d)", device, count);
+  SFM_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SFM_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("sfm_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+              prop.minor);
+    return SFM_ERR_UNSUPPORTED;
+  }
+  sfm_ctx* h = new sfm_ctx();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  *out = h;
+  return SFM_OK;
+}
+
+int sfm_destroy(sfm_handle_t h) {
+  if (!h) return SFM_OK;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+  return SFM_OK;
+}
+
+int sfm_load_superpoint(sfm_handle_t h, const float* packed, size_t n) {
+  SFM_REQUIRE(h && packed, "sfm_load_superpoint: NULL argument");
+  SFM_REQUIRE(n == sp_packed_floats(), "sfm_load_superpoint: expected %zu floats, got %zu", sp_packed_floats(), n);
+  SFM_CUDA(cudaSetDevice(h->device));
+  Reader r{packed, n};
+  for (int i = 0; i < 12; i++) {
+    const int cin = SP_DIMS[i][0], cout = SP_DIMS[i][1], k = SP_DIMS[i][2];
+    std::vector<float> w = r.take((size_t)cout * cin * k * k), b = r.take(cout);
+    std::vector<float> wk(w.size());
+    for (int o = 0; o < cout; o++)
+      for (int ci = 0; ci < cin; ci++)
+        for (int t = 0; t < k * k; t++)
+          wk[((size_t)o * k * k + t) * cin + ci] = w[((size_t)o * cin + ci) * k * k + t];
+    SpConv& c = h->sp.conv[i];
+    c.cin = cin; c.cout = cout; c.k = k;
+    SFM_TRY(upload(h, wk, &c.w));
+    SFM_TRY(upload(h, b, &c.b));
+  }
+  h->sp.loaded = true;
+  return SFM_OK;
+}
+
+int sfm_load_superglue(sfm_handle_t h, const float* packed, size_t n) {
+  SFM_REQUIRE(h && packed, "sfm_load_superglue: NULL argument");
+  SFM_REQUIRE(n == sg_packed_floats(), "sfm_load_superglue: expected %zu floats, got %zu", sg_packed_floats(), n);
+  SFM_CUDA(cudaSetDevice(h->device));
+  SgWeights& w = h->sg;
+  Reader r{packed, n};
+  w.bin_score = r.take(1)[0];
+  for (int i = 0; i < 5; i++) {
+    const int cin = KCH[i], cout = KCH[i + 1];
+    std::vector<float> W = r.take((size_t)cout * cin), b = r.take(cout);
+    int cin_p = cin;
+    if (i == 0) {  // pad K 3 -> 4
+      std::vector<float> Wp((size_t)cout * 4, 0.f);
+      for (int o = 0; o < cout; o++)
+        for (int c = 0; c < 3; c++) Wp[o * 4 + c] = W[o * 3 + c];
+      W.swap(Wp);
+      cin_p = 4;
+    }
+    SFM_TRY(upload(h, W, &w.kW[i]));
+    SFM_TRY(upload(h, b, &w.kb[i]));
+    if (i < 4) {
+      std::vector<float> g = r.take(cout), be = r.take(cout), rm = r.take(cout), rv = r.take(cout);
+      SFM_TRY(upload(h, g, &w.kbn[i].gamma));
+      SFM_TRY(upload(h, be, &w.kbn[i].beta));
+      SFM_TRY(upload(h, rm, &w.kbn[i].rmean));
+      SFM_TRY(upload(h, rv, &w.kbn[i].rvar));
+      std::vector<float> Wf, bf;
+      fold_bn(W, b, g, be, rm, rv, cout, cin_p, Wf, bf);
+      SFM_TRY(upload(h, Wf, &w.kWf[i]));
+      SFM_TRY(upload(h, bf, &w.kbf[i]));
+    }
+  }
+  int perm[256];
+  for (int c = 0; c < 256; c++) perm[c] = (c % 64) * 4 + c / 64;  // head-contiguous c' -> reference channel d*4+h
+  for (int l = 0; l < 18; l++) {
+    SgLayer& L = w.L[l];
+    std::vector<float> Wqkv((size_t)768 * 256), bqkv(768);
+    for (int j = 0; j < 3; j++) {
+      std::vector<float> W = r.take(256 * 256), b = r.take(256);
+      for (int c = 0; c < 256; c++) {
+        memcpy(&Wqkv[((size_t)j * 256 + c) * 256], &W[(size_t)perm[c] * 256], 256 * sizeof(float));
+        bqkv[j * 256 + c] = b[perm[c]];
+      }
+    }
+    std::vector<float> Wm = r.take(256 * 256), bm = r.take(256), Wmp(256 * 256);
+    for (int o = 0; o < 256; o++)
+      for (int c = 0; c < 256; c++) Wmp[o * 256 + c] = Wm[o * 256 + perm[c]];
+    std::vector<float> W1 = r.take(512 * 512), b1 = r.take(512);
+    std::vector<float> g = r.take(512), be = r.take(512), rm = r.take(512), rv = r.take(512);
+    std::vector<float> W2 = r.take(256 * 512), b2 = r.take(256);
+    std::vector<float> W1f, b1f;
+    fold_bn(W1, b1, g, be, rm, rv, 512, 512, W1f, b1f);
+    SFM_TRY(upload(h, Wqkv, &L.Wqkv)); SFM_TRY(upload(h, bqkv, &L.bqkv));
+    SFM_TRY(upload(h, Wmp, &L.Wm));    SFM_TRY(upload(h, bm, &L.bm));
+    SFM_TRY(upload(h, W1, &L.W1));     SFM_TRY(upload(h, b1, &L.b1));
+    SFM_TRY(upload(h, g, &L.bn1.gamma)); SFM_TRY(upload(h, be, &L.bn1.beta));
+    SFM_TRY(upload(h, rm, &L.bn1.rmean)); SFM_TRY(upload(h, rv, &L.bn1.rvar));
+    SFM_TRY(upload(h, W1f, &L.W1f));   SFM_TRY(upload(h, b1f, &L.b1f));
+    SFM_TRY(upload(h, W2, &L.W2));     SFM_TRY(upload(h, b2, &L.b2));
+    SFM_TRY(upload_bf16(h, Wqkv, &L.Wqkv_h));
+    SFM_TRY(upload_bf16(h, Wmp, &L.Wm_h));
+    SFM_TRY(upload_bf16(h, W1, &L.W1_h));
+    SFM_TRY(upload_bf16(h, W1f, &L.W1f_h));
+    SFM_TRY(upload_bf16(h, W2, &L.W2_h));
+  }
+  std::vector<float> Wf = r.take(256 * 256), bf = r.take(256);
+  SFM_TRY(upload(h, Wf, &w.Wf));
+  SFM_TRY(upload(h, bf, &w.bf));
+  SFM_TRY(upload_bf16(h, Wf, &w.Wf_h));
+  w.loaded = true;
+  return SFM_OK;
+}
+
+// ---- SuperPoint -------------------------------------------------------------------------------
+size_t sfm_superpoint_workspace_bytes(int n_img, int H, int W, int precision) {
+  size_t need = 0;
+  if (sp_forward_detect(nullptr, nullptr, n_img, H, W, nullptr, 0.f, 0, 0, precision, nullptr, nullptr, 0, true, &need,
+                        0) != SFM_OK)
+    return 0;
+  return need;
+}
+
+int sfm_superpoint_detect(sfm_handle_t h, const float* images, int n_img, int H, int W, const uint8_t* mask,
+                          float thr, int nms_radius, int border, int precision, int* cand_counts, void* ws,
+                          size_t ws_bytes, void* stream) {
+  SFM_REQUIRE(h, "sfm_superpoint_detect: NULL handle");
+  SFM_REQUIRE(n_img == 0 || images, "sfm_superpoint_detect: NULL images");
+  return sp_forward_detect(h, images, n_img, H, W, mask, thr, nms_radius, border, precision, cand_counts, ws, ws_bytes,
+                           false, nullptr, (cudaStream_t)stream);
+}
+
+int sfm_superpoint_describe(sfm_handle_t h, int n_img, int H, int W, int max_keypoints, int align_corners,
+                            int precision, int kp_cap, float* kpts_xy, float* scores, float* desc, int* counts,
+                            void* ws, size_t ws_bytes, void* stream) {
+  SFM_REQUIRE(h, "sfm_superpoint_describe: NULL handle");
+  return sp_forward_describe(h, n_img, H, W, max_keypoints, align_corners, precision, kp_cap, kpts_xy, scores, desc,
+                             counts, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int sfm_superpoint_tap(int n_img, int H, int W, int precision, int which, void* ws, size_t ws_bytes, float** out_ptr,
+                       size_t* out_floats) {
+  SFM_REQUIRE(out_ptr && out_floats, "sfm_superpoint_tap: NULL output");
+  return sp_tap(n_img, H, W, precision, which, ws, ws_bytes, out_ptr, out_floats);
+}
+
+int sfm_simple_nms(const float* scores, float* out, int n_img, int H, int W, int nms_radius, void* stream) {
+  SFM_REQUIRE(scores && out, "sfm_simple_nms: NULL argument");
+  return sp_nms(scores, out, n_img, H, W, nms_radius, (cudaStream_t)stream);
+}
+
+int sfm_sample_descriptors(const float* dmap_nhwc, int n_img, int h, int w, const float* kpts_xy, const int* counts,
+                           int kp_cap, int align_corners, float* desc, void* stream) {
+  SFM_REQUIRE(dmap_nhwc && kpts_xy && counts && desc, "sfm_sample_descriptors: NULL argument");
+  return sp_sample_descriptors(dmap_nhwc, n_img, h, w, kpts_xy, counts, kp_cap, align_corners, desc, kp_cap,
+                               (cudaStream_t)stream);
+}
+
+// ---- SuperGlue --------------------------------------------------------------------------------
+static SgCall shape_call(int B, int K0, int K1, int precision) {
+  SgCall c;
+  memset(&c, 0, sizeof(c));
+  c.B = B; c.K0 = K0; c.K1 = K1; c.precision = precision;
+  return c;
+}
+
+size_t sfm_superglue_workspace_bytes(int B, int K0, int K1, int precision) {
+  size_t need = 0;
+  SgCall c = shape_call(B, K0, K1, precision);
+  if (sg_forward(nullptr, c, nullptr, 0, true, &need, 0, nullptr, nullptr, 0) != SFM_OK) return 0;
+  return need;
+}
+
+int sfm_superglue_forward(sfm_handle_t h, const float* desc0, const float* kpts0, const float* scores0, int ldk0,
+                          int kcap0, const int* idx0, const float* desc1, const float* kpts1, const float* scores1,
+                          int ldk1, int kcap1, const int* idx1, int B, int K0, int K1, int H0, int W0, int H1, int W1,
+                          int sinkhorn_iterations, float match_threshold, int bn_mode, int precision,
+                          int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1, void* ws,
+                          size_t ws_bytes, void* stream) {
+  SFM_REQUIRE(h, "sfm_superglue_forward: NULL handle");
+  SFM_REQUIRE(B == 0 || (desc0 && kpts0 && scores0 && desc1 && kpts1 && scores1), "sfm_superglue_forward: NULL input");
+  SFM_REQUIRE(B == 0 || (matches0 && matches1 && mscores0 && mscores1), "sfm_superglue_forward: NULL output");
+  SFM_REQUIRE(K0 <= ldk0 && K0 <= kcap0 && K1 <= ldk1 && K1 <= kcap1, "sfm_superglue_forward: K exceeds record size");
+  SFM_REQUIRE(sinkhorn_iterations >= 0, "sfm_superglue_forward: negative sinkhorn_iterations");
+  SgCall c;
+  c.desc0 = desc0; c.kpts0 = kpts0; c.scores0 = scores0; c.ldk0 = ldk0; c.kcap0 = kcap0; c.idx0 = idx0;
+  c.desc1 = desc1; c.kpts1 = kpts1; c.scores1 = scores1; c.ldk1 = ldk1; c.kcap1 = kcap1; c.idx1 = idx1;
+  c.B = B; c.K0 = K0; c.K1 = K1; c.H0 = H0; c.W0 = W0; c.H1 = H1; c.W1 = W1;
+  c.iters = sinkhorn_iterations; c.thr = match_threshold; c.bn_mode = bn_mode; c.precision = precision;
+  c.m0 = (long long*)matches0; c.m1 = (long long*)matches1; c.ms0 = mscores0; c.ms1 = mscores1;
+  return sg_forward(h, c, ws, ws_bytes, false, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int sfm_superglue_tap(int B, int K0, int K1, int precision, int which, void* ws, size_t ws_bytes, float** out_ptr,
+                      size_t* out_floats) {
+  SFM_REQUIRE(out_ptr && out_floats, "sfm_superglue_tap: NULL output");
+  SgCall c = shape_call(B, K0, K1, precision);
+  return sg_forward(nullptr, c, ws, ws_bytes, false, nullptr, which, out_ptr, out_floats, 0);
+}
+
+// ---- optimal transport ------------------------------------------------------------------------
+namespace {
+struct OtBuffers {
+  float *u, *v, *part, *max0, *max1;
+  int *counters, *idx0, *idx1;
+  int R;
+};
+void ot_carve(Arena& a, int B, int N, int M, OtBuffers& b) {
+  b.u = a.get<float>((size_t)B * (N + 1));
+  b.v = a.get<float>((size_t)B * (M + 1));
+  b.part = a.get<float>(sinkhorn_partial_floats(B, N, M, &b.R));
+  b.counters = a.get<int>(sinkhorn_counter_ints(B, M));
+  b.max0 = a.get<float>((size_t)B * N);
+  b.max1 = a.get<float>((size_t)B * M);
+  b.idx0 = a.get<int>((size_t)B * N);
+  b.idx1 = a.get<int>((size_t)B * M);
+}
+int ot_prepare(const float* scores, int B, int N, int M, float alpha, int iters, void* ws, size_t ws_bytes,
+               OtBuffers& b, SinkhornArgs& s, cudaStream_t st) {
+  SFM_REQUIRE(scores && B >= 0 && N > 0 && M > 0 && iters >= 0, "sinkhorn: bad arguments (B=%d N=%d M=%d iters=%d)", B, N,
+              M, iters);
+  Arena a(ws, ws_bytes);
+  ot_carve(a, B, N, M, b);
+  if (a.overflow) {
+    set_error("sinkhorn: workspace too small (%zu bytes given, %zu needed)", ws_bytes, a.off);
+    return SFM_ERR_WORKSPACE;
+  }
+  SFM_CUDA(cudaMemsetAsync(b.counters, 0, sinkhorn_counter_ints(B, M) * sizeof(int), st));
+  s.S = scores; s.B = B; s.N = N; s.M = M; s.alpha = alpha; s.iters = iters;
+  s.u = b.u; s.v = b.v; s.part = b.part; s.counters = b.counters; s.R = b.R;
+  return sinkhorn_run(s, st);
+}
+}  // namespace
+
+size_t sfm_sinkhorn_workspace_bytes(int B, int N, int M) {
+  Arena a(nullptr, 0);
+  OtBuffers b;
+  ot_carve(a, B, N, M, b);
+  return a.off;
+}
+
+int sfm_log_optimal_transport(const float* scores, int B, int N, int M, float alpha, int iters, float* Z, void* ws,
+                              size_t ws_bytes, void* stream) {
+  SFM_REQUIRE(Z, "sfm_log_optimal_transport: NULL output");
+  OtBuffers b;
+  SinkhornArgs s;
+  SFM_TRY(ot_prepare(scores, B, N, M, alpha, iters, ws, ws_bytes, b, s, (cudaStream_t)stream));
+  return sinkhorn_write_Z(s, Z, (cudaStream_t)stream);
+}
+
+int sfm_sinkhorn_match(const float* scores, int B, int N, int M, float alpha, int iters, float match_threshold,
+                       int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1, void* ws,
+                       size_t ws_bytes, void* stream) {
+  SFM_REQUIRE(matches0 && matches1 && mscores0 && mscores1, "sfm_sinkhorn_match: NULL output");
+  OtBuffers b;
+  SinkhornArgs s;
+  SFM_TRY(ot_prepare(scores, B, N, M, alpha, iters, ws, ws_bytes, b, s, (cudaStream_t)stream));
+  return sinkhorn_match(s, match_threshold, b.max0, b.idx0, b.max1, b.idx1, (long long*)matches0, (long long*)matches1,
+                        mscores0, mscores1, (cudaStream_t)stream);
+}
+
+int sfm_compact_matches(const int64_t* matches0, int B, int K0, uint32_t* tables, int* lengths, void* stream) {
+  SFM_REQUIRE(B == 0 || (matches0 && tables && lengths), "sfm_compact_matches: NULL argument");
+  return compact_matches((const long long*)matches0, B, K0, tables, lengths, (cudaStream_t)stream);
+}
+
+// ---- SimpleMatcher ----------------------------------------------------------------------------
+namespace {
+struct SmBuffers {
+  float *x1, *x2, *dmat, *u, *v, *part, *max0, *max1;
+  int *counters, *idx0, *idx1;
+  int R;
+};
+void sm_carve(Arena& a, int N, int M, SmBuffers& b) {
+  b.x1 = a.get<float>((size_t)N * 256);
+  b.x2 = a.get<float>((size_t)M * 256);
+  b.dmat = a.get<float>((size_t)N * M);
+  b.u = a.get<float>(N + 1);
+  b.v = a.get<float>(M + 1);
+  b.part = a.get<float>(sinkhorn_partial_floats(1, N, M, &b.R));
+  b.counters = a.get<int>(sinkhorn_counter_ints(1, M));
+  b.max0 = a.get<float>(N);
+  b.max1 = a.get<float>(M);
+  b.idx0 = a.get<int>(N);
+  b.idx1 = a.get<int>(M);
+}
+}  // namespace
+
+size_t sfm_simple_match_workspace_bytes(int N, int M) {
+  Arena a(nullptr, 0);
+  SmBuffers b;
+  sm_carve(a, N, M, b);
+  return a.off;
+}
+
+int sfm_simple_match(const float* desc1, int ld1, int N, const float* desc2, int ld2, int M, float nn_thresh,
+                     float* out, int out_ld, int* count, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SFM_REQUIRE(desc1 && desc2 && out && count, "sfm_simple_match: NULL argument");
+  SFM_REQUIRE(N > 0 && M > 0, "sfm_simple_match: empty descriptor set");
+  if (nn_thresh < 0.f) {
+    set_error("'nn_thresh' should be non-negative");
+    return SFM_ERR_INVALID;
+  }
+  Arena a(ws, ws_bytes);
+  SmBuffers b;
+  sm_carve(a, N, M, b);
+  if (a.overflow) {
+    set_error("simple_match: workspace too small (%zu bytes given, %zu needed)", ws_bytes, a.off);
+    return SFM_ERR_WORKSPACE;
+  }
+  SFM_CUDA(cudaMemsetAsync(b.counters, 0, sinkhorn_counter_ints(1, M) * sizeof(int), st));
+  SFM_CUDA(cudaMemsetAsync(b.u, 0, (N + 1) * sizeof(float), st));
+  SFM_CUDA(cudaMemsetAsync(b.v, 0, (M + 1) * sizeof(float), st));
+  SFM_TRY(transpose_to_tokens(desc1, ld1, N, b.x1, st));
+  SFM_TRY(transpose_to_tokens(desc2, ld2, M, b.x2, st));
+  GemmF32 g;
+  g.A = b.x1; g.lda = 256; g.B = b.x2; g.ldb = 256; g.C = b.dmat; g.ldc = M;
+  g.M = N; g.N = M; g.K = 256;
+  SFM_TRY(gemm_f32_nt(g, st));
+  SFM_TRY(neg_l2_from_dot(b.dmat, (long long)N * M, st));
+  SinkhornArgs s;
+  s.S = b.dmat; s.B = 1; s.N = N; s.M = M; s.alpha = 0.f; s.iters = 0;
+  s.u = b.u; s.v = b.v; s.part = b.part; s.counters = b.counters; s.R = b.R;
+  SFM_TRY(argmax_rows_cols(s, 0.f, b.max0, b.idx0, b.max1, b.idx1, st));
+  return simple_mutual(b.max0, b.idx0, b.idx1, N, nn_thresh, out, out_ld, count, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// Handle: packed weights resident on one device.  Internal.
+#pragma once
+#include <vector>
+#include "common.cuh"
+
+namespace sfm {
+
+struct SpConv {
+  int cin, cout, k;
+  float* w;  // [cout][k*k*cin]  (ky, kx, ci) K-major  -- implicit-GEMM B operand
+  float* b;  // [cout]
+};
+
+struct SgBn {
+  float *gamma, *beta, *rmean, *rvar;
+};
+
+struct SgLayer {
+  float* Wqkv;   // [768, 256] rows: q (head-contiguous), k, v
+  float* bqkv;   // [768]
+  float* Wm;     // [256, 256] input columns head-contiguous
+  float* bm;
+  float* W1;     // [512, 512]
+  float* b1;
+  SgBn bn1;
+  float* W1f;    // eval-mode BN folded into W1/b1
+  float* b1f;
+  float* W2;     // [256, 512]
+  float* b2;
+  // bf16 copies for the tcgen05 path
+  __nv_bfloat16 *Wqkv_h, *Wm_h, *W1_h, *W1f_h, *W2_h;
+};
+
+struct SgWeights {
+  bool loaded = false;
+  float bin_score = 1.f;
+  int kch[6] = {4, 32, 64, 128, 256, 256};  // first layer K padded 3 -> 4
+  float* kW[5];
+  float* kb[5];
+  SgBn kbn[4];
+  float* kWf[4];  // eval-folded
+  float* kbf[4];
+  SgLayer L[18];
+  float* Wf;
+  float* bf;
+  __nv_bfloat16* Wf_h;
+};
+
+struct SpWeights {
+  bool loaded = false;
+  SpConv conv[12];
+};
+
+}  // namespace sfm
+
+struct sfm_ctx {
+  int device = 0;
+  int sm_count = 148;
+  sfm::SpWeights sp;
+  sfm::SgWeights sg;
+  std::vector<void*> allocs;  // everything cudaMalloc'ed by the handle
+};
+
+namespace sfm {
+int sp_forward_detect(sfm_ctx* h, const float* images, int n_img, int H, int W, const unsigned char* mask, float thr,
+                      int nms_radius, int border, int precision, int* cand_counts, void* ws, size_t ws_bytes,
+                      bool dry, size_t* need, cudaStream_t st);
+int sp_forward_describe(sfm_ctx* h, int n_img, int H, int W, int max_kp, int align_corners, int precision, int kp_cap,
+                        float* kpts_xy, float* scores, float* desc, int* counts, void* ws, size_t ws_bytes,
+                        cudaStream_t st);
+int sp_tap(int n_img, int H, int W, int precision, int which, void* ws, size_t ws_bytes, float** out, size_t* n);
+
+struct SgCall {
+  const float *desc0, *kpts0, *scores0;
+  int ldk0, kcap0;
+  const int* idx0;
+  const float *desc1, *kpts1, *scores1;
+  int ldk1, kcap1;
+  const int* idx1;
+  int B, K0, K1, H0, W0, H1, W1;
+  int iters;
+  float thr;
+  int bn_mode, precision;
+  long long *m0, *m1;
+  float *ms0, *ms1;
+};
+// dry = true: only compute the workspace size / tap offsets (no launches, h may be null)
+int sg_forward(sfm_ctx* h, const SgCall& c, void* ws, size_t ws_bytes, bool dry, size_t* need, int tap_which,
+               float** tap_ptr, size_t* tap_floats, cudaStream_t st);
+}  // namespace sfm

@@ -1,0 +1,634 @@
+#include "sg_kernels.cuh"
+
+namespace sfm {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) frontend_kernel(const float* __restrict__ desc, long long img_stride, int ldk,
+                                                       const float* __restrict__ kpts,
+                                                       const float* __restrict__ scores, int kcap,
+                                                       const int* __restrict__ idx, int K, int imgH, int imgW,
+                                                       float* __restrict__ X, float* __restrict__ kin) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.y;
+  const int img = idx ? idx[b] : b;
+  const int k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* d = desc + (long long)img * img_stride;
+  for (int cb = 0; cb < 8; cb++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      int c = cb * 32 + ty * 4 + r;
+      int k = k0 + tx;
+      tile[ty * 4 + r][tx] = k < K ? d[(long long)c * ldk + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      int k = k0 + ty * 4 + r;
+      if (k < K) X[((long long)b * K + k) * 256 + cb * 32 + tx] = tile[tx][ty * 4 + r];
+    }
+    __syncthreads();
+  }
+  if (kin != nullptr && threadIdx.x < 32) {
+    int k = k0 + threadIdx.x;
+    if (k < K) {
+      // normalize_keypoints: (kp - size/2) / (0.7 * max(W, H))   superglue.py:62-69
+      float w = (float)imgW, h = (float)imgH;
+      float scaling = __fmul_rn(fmaxf(w, h), 0.7f);
+      float x = kpts[((long long)img * kcap + k) * 2 + 0];
+      float y = kpts[((long long)img * kcap + k) * 2 + 1];
+      float4 o;
+      o.x = __fdiv_rn(__fsub_rn(x, __fdiv_rn(w, 2.f)), scaling);
+      o.y = __fdiv_rn(__fsub_rn(y, __fdiv_rn(h, 2.f)), scaling);
+      o.z = scores[(long long)img * kcap + k];
+      o.w = 0.f;
+      reinterpret_cast<float4*>(kin)[(long long)b * K + k] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ X, int ld, int C, int g0_rows,
+                                                        int g1_rows, float* __restrict__ mean,
+                                                        float* __restrict__ var) {
+  __shared__ float red[8][33];
+  __shared__ float smean[32];
+  const int g = blockIdx.y;
+  const int r0 = g == 0 ? 0 : g0_rows;
+  const int n = g == 0 ? g0_rows : g1_rows;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const bool ok = c < C;
+  const float* base = X + (long long)r0 * ld + c;
+  float s = 0.f;
+  if (ok)
+    for (int r = ty; r < n; r += 8) s += base[(long long)r * ld];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) t += red[k][tx];
+    smean[tx] = n > 0 ? t / (float)n : 0.f;
+  }
+  __syncthreads();
+  const float mu = smean[tx];
+  s = 0.f;
+  if (ok)
+    for (int r = ty; r < n; r += 8) {
+      float dlt = base[(long long)r * ld] - mu;
+      s = fmaf(dlt, dlt, s);
+    }
+  __syncthreads();
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && ok) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) t += red[k][tx];
+    mean[g * C + c] = mu;
+    var[g * C + c] = n > 0 ? t / (float)n : 0.f;
+  }
+}
+
+__global__ void bn_relu_kernel(float* __restrict__ X, int ld, int C4, int g0_rows, long long total4,
+                               const float* __restrict__ mean, const float* __restrict__ var,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total4) return;
+  int c4 = gid % C4;
+  long long row = gid / C4;
+  int g = row >= g0_rows ? 1 : 0;
+  int C = C4 * 4;
+  float4 x = *reinterpret_cast<float4*>(X + row * ld + c4 * 4);
+  float4 mu = *reinterpret_cast<const float4*>(mean + g * C + c4 * 4);
+  float4 vr = *reinterpret_cast<const float4*>(var + g * C + c4 * 4);
+  float4 ga = *reinterpret_cast<const float4*>(gamma + c4 * 4);
+  float4 be = *reinterpret_cast<const float4*>(beta + c4 * 4);
+  auto f = [eps](float xv, float m, float v, float gm, float bt) {
+    float a = gm * (1.0f / sqrtf(v + eps));
+    return fmaxf(fmaf(xv - m, a, bt), 0.f);
+  };
+  x.x = f(x.x, mu.x, vr.x, ga.x, be.x);
+  x.y = f(x.y, mu.y, vr.y, ga.y, be.y);
+  x.z = f(x.z, mu.z, vr.z, ga.z, be.z);
+  x.w = f(x.w, mu.w, vr.w, ga.w, be.w);
+  *reinterpret_cast<float4*>(X + row * ld + c4 * 4) = x;
+}
+
+__global__ void softmax_rows_kernel(float* __restrict__ S, long long rows, int M, int ld) {
+  long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* p = S + row * ld;
+  float m = -INFINITY;
+  for (int j = lane; j < M; j += 32) m = fmaxf(m, p[j]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int j = lane; j < M; j += 32) {
+    float e = expf(p[j] - m);
+    p[j] = e;
+    s += e;
+  }
+  s = warp_sum(s);
+  for (int j = lane; j < M; j += 32) p[j] = p[j] / s;
+  for (int j = M + lane; j < ld; j += 32) p[j] = 0.f;   // keep the row padding at zero (GEMM reads float4)
+}
+
+// ------------------------------------------------------------------------------------------
+// Sinkhorn.  Z = [[S, a], [a, a]] is never built: the dustbin row/column are the constant a.
+__device__ __forceinline__ void lse_push(float& m, float& s, float x) {
+  if (x > m) {
+    s = s * expf(m - x) + 1.f;
+    m = x;
+  } else {
+    s += expf(x - m);
+  }
+}
+__device__ __forceinline__ void lse_join(float& m, float& s, float m2, float s2) {
+  float mm = fmaxf(m, m2);
+  if (mm == -INFINITY) {
+    s = 0.f;
+    m = mm;
+    return;
+  }
+  s = s * expf(m - mm) + s2 * expf(m2 - mm);
+  m = mm;
+}
+
+// u_i = log_mu_i - LSE_j(Z_ij + v_j); one warp per row (rows 0..N, row N is the dustbin row)
+__global__ void __launch_bounds__(256) sk_row_kernel(const float* __restrict__ S, int N, int M, float alpha,
+                                                     const float* __restrict__ v, float* __restrict__ u, float norm,
+                                                     float log_mu_bin) {
+  const int b = blockIdx.y;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row > N) return;
+  const float* vb = v + (long long)b * (M + 1);
+  float m = -INFINITY, s = 0.f;
+  if (row < N) {
+    const float* sr = S + ((long long)b * N + row) * M;
+    int j = lane;
+    for (; j + 96 < M; j += 128) {
+      float x0 = sr[j] + vb[j], x1 = sr[j + 32] + vb[j + 32], x2 = sr[j + 64] + vb[j + 64],
+            x3 = sr[j + 96] + vb[j + 96];
+      float cm = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+      if (cm > m) {
+        s *= expf(m - cm);
+        m = cm;
+      }
+      s += expf(x0 - m) + expf(x1 - m) + expf(x2 - m) + expf(x3 - m);
+    }
+    for (; j < M; j += 32) lse_push(m, s, sr[j] + vb[j]);
+  } else {
+    for (int j = lane; j < M; j += 32) lse_push(m, s, alpha + vb[j]);
+  }
+  if (lane == 0) lse_push(m, s, alpha + vb[M]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    lse_join(m, s, m2, s2);
+  }
+  if (lane == 0) u[(long long)b * (N + 1) + row] = (row < N ? norm : log_mu_bin) - (m + logf(s));
+}
+
+// column pass.  MODE 0: v_j = log_nu_j - LSE_i(Z_ij + u_i).  MODE 1: column argmax of
+// ((S_ij + u_i) + v_j) - norm over i < N (first index on ties).
+// grid (colblocks(128), R, B), 256 threads: warp w takes rows r0 + w, r0 + w + 8, ...
+template <int MODE>
+__global__ void __launch_bounds__(256) sk_col_kernel(const float* __restrict__ S, int N, int M, float alpha,
+                                                     const float* __restrict__ u, const float* __restrict__ vin,
+                                                     float* __restrict__ out_v, float* __restrict__ part,
+                                                     int* __restrict__ counters, int R, float norm, float log_nu_bin,
+                                                     float* __restrict__ max1, int* __restrict__ idx1) {
+  __shared__ float sm_m[8][128];
+  __shared__ float sm_s[8][128];   // MODE 1: bit pattern of the row index
+  __shared__ int is_last;
+  const int b = blockIdx.z, split = blockIdx.y, cb = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows_per = (N + R - 1) / R;
+  const int r0 = split * rows_per, r1 = min(N, r0 + rows_per);
+  const float* ub = u + (long long)b * (N + 1);
+  const float* Sb = S + (long long)b * N * M;
+  const int c0 = cb * 128;
+  float m[4], s[4];
+  int bi[4];
+  float vj[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    m[q] = -INFINITY;
+    s[q] = 0.f;
+    bi[q] = 0x7fffffff;
+    int j = c0 + lane + 32 * q;
+    vj[q] = (MODE == 1 && j < M) ? vin[(long long)b * (M + 1) + j] : 0.f;
+  }
+  for (int i = r0 + warp; i < r1; i += 8) {
+    const float ui = ub[i];
+    const float* sr = Sb + (long long)i * M + c0 + lane;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      int j = c0 + lane + 32 * q;
+      if (j < M) {
+        if (MODE == 0) {
+          lse_push(m[q], s[q], sr[32 * q] + ui);
+        } else {
+          float z = __fsub_rn(__fadd_rn(__fadd_rn(sr[32 * q], ui), vj[q]), norm);
+          if (z > m[q]) {
+            m[q] = z;
+            bi[q] = i;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    sm_m[warp][lane + 32 * q] = m[q];
+    sm_s[warp][lane + 32 * q] = MODE == 0 ? s[q] : __int_as_float(bi[q]);
+  }
+  __syncthreads();
+  const int pstride = (M + 1) * 2;
+  float* pb = part + ((long long)b * R + split) * pstride;
+  if (threadIdx.x < 128) {
+    int j = c0 + threadIdx.x;
+    if (j < M) {
+      float mm = sm_m[0][threadIdx.x], ss = sm_s[0][threadIdx.x];
+      for (int w = 1; w < 8; w++) {
+        float m2 = sm_m[w][threadIdx.x], s2 = sm_s[w][threadIdx.x];
+        if (MODE == 0) {
+          lse_join(mm, ss, m2, s2);
+        } else {
+          int i1 = __float_as_int(ss), i2 = __float_as_int(s2);
+          if (m2 > mm || (m2 == mm && i2 < i1)) {
+            mm = m2;
+            ss = s2;
+          }
+        }
+      }
+      __stcg(&pb[2 * j], mm);
+      __stcg(&pb[2 * j + 1], ss);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int prev = atomicAdd(&counters[b * gridDim.x + cb], 1);
+    is_last = (prev == R - 1);
+    if (is_last) counters[b * gridDim.x + cb] = 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float* p0 = part + (long long)b * R * pstride;
+  if (threadIdx.x < 128) {
+    int j = c0 + threadIdx.x;
+    if (j < M) {
+      float mm = __ldcg(&p0[2 * j]), ss = __ldcg(&p0[2 * j + 1]);
+      for (int r = 1; r < R; r++) {
+        float m2 = __ldcg(&p0[(long long)r * pstride + 2 * j]), s2 = __ldcg(&p0[(long long)r * pstride + 2 * j + 1]);
+        if (MODE == 0) {
+          lse_join(mm, ss, m2, s2);
+        } else {
+          int i1 = __float_as_int(ss), i2 = __float_as_int(s2);
+          if (m2 > mm || (m2 == mm && i2 < i1)) {
+            mm = m2;
+            ss = s2;
+          }
+        }
+      }
+      if (MODE == 0) {
+        lse_join(mm, ss, alpha + ub[N], 1.f);   // dustbin row
+        out_v[(long long)b * (M + 1) + j] = norm - (mm + logf(ss));
+      } else {
+        int bidx = __float_as_int(ss);
+        max1[(long long)b * M + j] = mm;
+        idx1[(long long)b * M + j] = bidx == 0x7fffffff ? 0 : bidx;
+      }
+    }
+  }
+  if (MODE == 0 && cb == 0) {
+    // dustbin column: LSE_i(alpha + u_i), i = 0..N
+    float mm = -INFINITY, ss = 0.f;
+    for (int i = threadIdx.x; i <= N; i += 256) lse_push(mm, ss, alpha + ub[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float m2 = __shfl_xor_sync(0xffffffffu, mm, o), s2 = __shfl_xor_sync(0xffffffffu, ss, o);
+      lse_join(mm, ss, m2, s2);
+    }
+    __syncthreads();
+    if (lane == 0) {
+      sm_m[0][warp] = mm;
+      sm_s[0][warp] = ss;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; w++) lse_join(mm, ss, sm_m[0][w], sm_s[0][w]);
+      out_v[(long long)b * (M + 1) + M] = log_nu_bin - (mm + logf(ss));
+    }
+  }
+}
+
+// row argmax of ((S_ij + u_i) + v_j) - norm over j < M, first index on ties; one warp per row
+__global__ void __launch_bounds__(256) sk_row_argmax_kernel(const float* __restrict__ S, int N, int M,
+                                                            const float* __restrict__ u, const float* __restrict__ v,
+                                                            float norm, float* __restrict__ max0,
+                                                            int* __restrict__ idx0) {
+  const int b = blockIdx.y;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* sr = S + ((long long)b * N + row) * M;
+  const float* vb = v + (long long)b * (M + 1);
+  const float ui = u[(long long)b * (N + 1) + row];
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = lane; j < M; j += 32) {
+    float z = __fsub_rn(__fadd_rn(__fadd_rn(sr[j], ui), vb[j]), norm);
+    if (z > best) {
+      best = z;
+      bi = j;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+    int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (b2 > best || (b2 == best && i2 < bi)) {
+      best = b2;
+      bi = i2;
+    }
+  }
+  if (lane == 0) {
+    max0[(long long)b * N + row] = best;
+    idx0[(long long)b * N + row] = bi == 0x7fffffff ? 0 : bi;
+  }
+}
+
+__global__ void mutual_kernel(const float* __restrict__ max0, const int* __restrict__ idx0,
+                              const int* __restrict__ idx1, int N, int M, float thr, long long* __restrict__ m0,
+                              long long* __restrict__ m1, float* __restrict__ ms0, float* __restrict__ ms1) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* mx = max0 + (long long)b * N;
+  const int* i0 = idx0 + (long long)b * N;
+  const int* i1 = idx1 + (long long)b * M;
+  if (t < N) {
+    int j = i0[t];
+    bool mutual = (i1[j] == t);
+    float sc = mutual ? expf(mx[t]) : 0.f;
+    bool valid = mutual && sc > thr;
+    m0[(long long)b * N + t] = valid ? (long long)j : -1ll;
+    ms0[(long long)b * N + t] = sc;
+  }
+  if (t < M) {
+    int i = i1[t];
+    bool mutual1 = (i0[i] == t);
+    bool mutual0 = (i1[i0[i]] == i);
+    float sc0 = mutual0 ? expf(mx[i]) : 0.f;
+    bool valid0 = mutual0 && sc0 > thr;
+    m1[(long long)b * M + t] = (mutual1 && valid0) ? (long long)i : -1ll;
+    ms1[(long long)b * M + t] = mutual1 ? sc0 : 0.f;
+  }
+}
+
+__global__ void write_Z_kernel(const float* __restrict__ S, int N, int M, float alpha, const float* __restrict__ u,
+                               const float* __restrict__ v, float norm, float* __restrict__ Z) {
+  const int b = blockIdx.z;
+  const int i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > M) return;
+  float c = (i < N && j < M) ? S[((long long)b * N + i) * M + j] : alpha;
+  float z = __fsub_rn(__fadd_rn(__fadd_rn(c, u[(long long)b * (N + 1) + i]), v[(long long)b * (M + 1) + j]), norm);
+  Z[((long long)b * (N + 1) + i) * (M + 1) + j] = z;
+}
+
+__global__ void fill_kernel(float* p, long long n, float v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// one block per pair: ordered compaction of valid rows
+__global__ void __launch_bounds__(256) compact_kernel(const long long* __restrict__ m0, int N,
+                                                      unsigned* __restrict__ tables, int* __restrict__ lengths) {
+  const int b = blockIdx.x;
+  const long long* m = m0 + (long long)b * N;
+  unsigned* out = tables + (long long)b * N * 2;
+  __shared__ int wsums[8];
+  __shared__ int running;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  for (int base = 0; base < N; base += 256) {
+    int i = base + threadIdx.x;
+    long long mv = i < N ? m[i] : -1ll;
+    bool keep = mv > -1;
+    unsigned bal = __ballot_sync(0xffffffffu, keep);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) wsums[wid] = __popc(bal);
+    __syncthreads();
+    int off = running;
+    for (int k = 0; k < wid; k++) off += wsums[k];
+    off += __popc(bal & ((1u << lane) - 1));
+    if (keep) {
+      out[2 * off] = (unsigned)i;
+      out[2 * off + 1] = (unsigned)mv;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int k = 0; k < 8; k++) t += wsums[k];
+      running += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) lengths[b] = running;
+}
+
+// SimpleMatcher: S <- -sqrt(2 - 2 clamp(S, -1, 1))   (simple_matcher.py:89-90; negated so argmax == argmin)
+__global__ void neg_l2_kernel(float* __restrict__ S, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float d = fminf(fmaxf(S[i], -1.f), 1.f);
+    S[i] = -sqrtf(__fsub_rn(2.f, __fmul_rn(2.f, d)));
+  }
+}
+
+// keep i when dist_i < thr and the nearest neighbour is mutual; ordered compaction into (3, L)
+__global__ void __launch_bounds__(256) simple_mutual_kernel(const float* __restrict__ max0,
+                                                            const int* __restrict__ idx0,
+                                                            const int* __restrict__ idx1, int N, float thr,
+                                                            float* __restrict__ out, int ld, int* __restrict__ count) {
+  __shared__ int wsums[8];
+  __shared__ int running;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  for (int base = 0; base < N; base += 256) {
+    int i = base + threadIdx.x;
+    bool keep = false;
+    int j = 0;
+    float d = 0.f;
+    if (i < N) {
+      j = idx0[i];
+      d = -max0[i];
+      keep = (d < thr) && (idx1[j] == i);
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, keep);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) wsums[wid] = __popc(bal);
+    __syncthreads();
+    int off = running;
+    for (int k = 0; k < wid; k++) off += wsums[k];
+    off += __popc(bal & ((1u << lane) - 1));
+    if (keep && off < ld) {
+      out[off] = (float)i;
+      out[ld + off] = (float)j;
+      out[2 * ld + off] = d;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int k = 0; k < 8; k++) t += wsums[k];
+      running += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = running;
+}
+
+}  // namespace
+
+int transpose_to_tokens(const float* desc, int ld, int N, float* X, cudaStream_t st) {
+  return sg_frontend(desc, 0, ld, nullptr, nullptr, 0, nullptr, 1, N, 0, 0, X, nullptr, st);
+}
+
+int neg_l2_from_dot(float* S, long long n, cudaStream_t st) {
+  if (n == 0) return SFM_OK;
+  neg_l2_kernel<<<cdiv(n, 256), 256, 0, st>>>(S, n);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+int simple_mutual(const float* max0, const int* idx0, const int* idx1, int N, float thr, float* out, int ld,
+                  int* count, cudaStream_t st) {
+  simple_mutual_kernel<<<1, 256, 0, st>>>(max0, idx0, idx1, N, thr, out, ld, count);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+int sg_frontend(const float* desc, long long desc_img_stride, int ldk, const float* kpts, const float* scores,
+                int kcap, const int* idx, int B, int K, int imgH, int imgW, float* X, float* kin, cudaStream_t st) {
+  if (B == 0 || K == 0) return SFM_OK;
+  dim3 grid(cdiv(K, 32), B);
+  frontend_kernel<<<grid, 256, 0, st>>>(desc, desc_img_stride, ldk, kpts, scores, kcap, idx, K, imgH, imgW, X, kin);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+int col_stats_f32(const float* X, int ld, int C, int g0_rows, int g1_rows, float* mean, float* var,
+                  cudaStream_t st) {
+  dim3 grid(cdiv(C, 32), 2);
+  col_stats_kernel<<<grid, 256, 0, st>>>(X, ld, C, g0_rows, g1_rows, mean, var);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+int bn_relu_f32(float* X, int ld, int C, int g0_rows, int g1_rows, const float* mean, const float* var,
+                const float* gamma, const float* beta, float eps, cudaStream_t st) {
+  SFM_REQUIRE(C % 4 == 0 && ld % 4 == 0, "bn_relu: C and ld must be multiples of 4");
+  long long total4 = (long long)(g0_rows + g1_rows) * (C / 4);
+  if (total4 == 0) return SFM_OK;
+  bn_relu_kernel<<<cdiv(total4, 256), 256, 0, st>>>(X, ld, C / 4, g0_rows, total4, mean, var, gamma, beta, eps);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+int softmax_rows_f32(float* S, long long rows, int M, int ld, cudaStream_t st) {
+  if (rows == 0 || M == 0) return SFM_OK;
+  softmax_rows_kernel<<<cdiv(rows * 32, 256), 256, 0, st>>>(S, rows, M, ld);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+static int pick_R(int B, int N, int M) {
+  int colblocks = cdiv(M, 128);
+  long long base = (long long)B * colblocks;
+  int R = (int)((148 * 4 + base - 1) / base);
+  int maxR = (N + 63) / 64;
+  if (R > maxR) R = maxR;
+  if (R < 1) R = 1;
+  return R;
+}
+
+size_t sinkhorn_partial_floats(int B, int N, int M, int* R_out) {
+  int R = pick_R(B, N, M);
+  if (R_out) *R_out = R;
+  return (size_t)B * R * (M + 1) * 2;
+}
+size_t sinkhorn_counter_ints(int B, int M) { return (size_t)B * cdiv(M, 128); }
+
+int sinkhorn_run(const SinkhornArgs& a, cudaStream_t st) {
+  const int B = a.B, N = a.N, M = a.M;
+  if (B == 0) return SFM_OK;
+  SFM_REQUIRE(N > 0 && M > 0, "sinkhorn: empty side");
+  // constants as the reference computes them in float32 (superglue.py:165-167)
+  const float norm = -logf((float)N + (float)M);
+  const float log_mu_bin = logf((float)M) + norm;
+  const float log_nu_bin = logf((float)N) + norm;
+  long long nv = (long long)B * (M + 1), nu = (long long)B * (N + 1);
+  fill_kernel<<<cdiv(nv, 256), 256, 0, st>>>(a.v, nv, 0.f);
+  fill_kernel<<<cdiv(nu, 256), 256, 0, st>>>(a.u, nu, 0.f);
+  SFM_LAUNCH_CHECK();
+  dim3 rgrid(cdiv(N + 1, 8), B);
+  dim3 cgrid(cdiv(M, 128), a.R, B);
+  for (int it = 0; it < a.iters; it++) {
+    sk_row_kernel<<<rgrid, 256, 0, st>>>(a.S, N, M, a.alpha, a.v, a.u, norm, log_mu_bin);
+    sk_col_kernel<0><<<cgrid, 256, 0, st>>>(a.S, N, M, a.alpha, a.u, nullptr, a.v, a.part, a.counters, a.R, norm,
+                                            log_nu_bin, nullptr, nullptr);
+  }
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+int argmax_rows_cols(const SinkhornArgs& a, float norm, float* max0, int* idx0, float* max1, int* idx1,
+                     cudaStream_t st) {
+  const int B = a.B, N = a.N, M = a.M;
+  if (B == 0) return SFM_OK;
+  dim3 rgrid(cdiv(N, 8), B);
+  sk_row_argmax_kernel<<<rgrid, 256, 0, st>>>(a.S, N, M, a.u, a.v, norm, max0, idx0);
+  dim3 cgrid(cdiv(M, 128), a.R, B);
+  sk_col_kernel<1><<<cgrid, 256, 0, st>>>(a.S, N, M, a.alpha, a.u, a.v, nullptr, a.part, a.counters, a.R, norm, 0.f,
+                                          max1, idx1);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+int sinkhorn_match(const SinkhornArgs& a, float thr, float* max0, int* idx0, float* max1, int* idx1,
+                   long long* matches0, long long* matches1, float* mscores0, float* mscores1, cudaStream_t st) {
+  const int B = a.B, N = a.N, M = a.M;
+  if (B == 0) return SFM_OK;
+  const float norm = -logf((float)N + (float)M);
+  SFM_TRY(argmax_rows_cols(a, norm, max0, idx0, max1, idx1, st));
+  dim3 mgrid(cdiv(N > M ? N : M, 256), B);
+  mutual_kernel<<<mgrid, 256, 0, st>>>(max0, idx0, idx1, N, M, thr, matches0, matches1, mscores0, mscores1);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+int sinkhorn_write_Z(const SinkhornArgs& a, float* Z, cudaStream_t st) {
+  if (a.B == 0) return SFM_OK;
+  const float norm = -logf((float)a.N + (float)a.M);
+  dim3 grid(cdiv(a.M + 1, 256), a.N + 1, a.B);
+  write_Z_kernel<<<grid, 256, 0, st>>>(a.S, a.N, a.M, a.alpha, a.u, a.v, norm, Z);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+int compact_matches(const long long* matches0, int B, int N, unsigned* tables, int* lengths, cudaStream_t st) {
+  if (B == 0) return SFM_OK;
+  compact_kernel<<<B, 256, 0, st>>>(matches0, N, tables, lengths);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+}  // namespace sfm

@@ -1,0 +1,58 @@
+// SuperGlue element-wise / reduction kernels shared by the fp32 and bf16 paths.
+#pragma once
+#include "common.cuh"
+
+namespace sfm {
+
+// Gather one batch of pairs from per-image feature records into token-major activations.
+//   desc  : per image channel-major (256, ldk) f32 (reference Frame layout), image stride img_stride
+//   kpts  : per image (kcap, 2) f32; scores: per image (kcap,)
+//   idx   : device int32 [B] image index of each pair's side, or nullptr for identity
+//   X     : [B*K, 256] token-major descriptors (f32)
+//   kin   : [B*K, 4]   (x_norm, y_norm, score, 0)  -- keypoint-encoder input (superglue.py:62-82)
+int sg_frontend(const float* desc, long long desc_img_stride, int ldk, const float* kpts, const float* scores,
+                int kcap, const int* idx, int B, int K, int imgH, int imgW, float* X, float* kin,
+                cudaStream_t st);
+
+// per-channel batch statistics over token groups (train-mode BatchNorm1d, superglue.py:56-57)
+//   X [T, C] (ld), groups g: rows [gstart[g], gstart[g+1]);  mean/var: [G, C] (biased variance)
+int col_stats_f32(const float* X, int ld, int C, int g0_rows, int g1_rows, float* mean, float* var,
+                  cudaStream_t st);
+// X = relu((X - mean) * rsqrt(var + eps) * gamma + beta), in place, per group
+int bn_relu_f32(float* X, int ld, int C, int g0_rows, int g1_rows, const float* mean, const float* var,
+                const float* gamma, const float* beta, float eps, cudaStream_t st);
+// in-place softmax over the last dim of [rows, M] (ld)
+int softmax_rows_f32(float* S, long long rows, int M, int ld, cudaStream_t st);
+
+// ---- optimal transport + matching (superglue.py:142-171, 273-283)
+struct SinkhornArgs {
+  const float* S;   // [B, N, M] scores (already divided by sqrt(d))
+  int B, N, M;
+  float alpha;      // bin_score
+  int iters;
+  float* u;         // [B, N+1]
+  float* v;         // [B, M+1]
+  float* part;      // [B, R, M+1, 2] column partials
+  int* counters;    // [B, colblocks] zero-initialised, self-resetting
+  int R;            // row splits of the column pass
+};
+size_t sinkhorn_partial_floats(int B, int N, int M, int* R_out);
+size_t sinkhorn_counter_ints(int B, int M);
+int sinkhorn_run(const SinkhornArgs& a, cudaStream_t st);
+// mutual nearest neighbour + threshold from S, u, v  (never materialises the (N+1)x(M+1) matrix)
+int sinkhorn_match(const SinkhornArgs& a, float match_threshold, float* max0, int* idx0, float* max1, int* idx1,
+                   long long* matches0, long long* matches1, float* mscores0, float* mscores1, cudaStream_t st);
+int argmax_rows_cols(const SinkhornArgs& a, float norm, float* max0, int* idx0, float* max1, int* idx1,
+                     cudaStream_t st);
+// SimpleMatcher pieces (simple_matcher.py:66-114)
+int transpose_to_tokens(const float* desc, int ld, int N, float* X, cudaStream_t st);
+int neg_l2_from_dot(float* S, long long n, cudaStream_t st);
+int simple_mutual(const float* max0, const int* idx0, const int* idx1, int N, float thr, float* out, int ld,
+                  int* count, cudaStream_t st);
+// optional: write the full (B, N+1, M+1) log-assignment (what log_optimal_transport returns)
+int sinkhorn_write_Z(const SinkhornArgs& a, float* Z, cudaStream_t st);
+
+// (L,2) uint32 match-table compaction per pair: rows [i, matches0[i]] for matches0[i] > -1
+int compact_matches(const long long* matches0, int B, int N, unsigned* tables, int* lengths, cudaStream_t st);
+
+}  // namespace sfm

@@ -1,0 +1,311 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every call goes through the C ABI of
+libsfm_b200.so; results are compared with the golden vectors of the unmodified reference and
+with the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): keypoint indices and mutual-match indices bit-exact in fp32;
+descriptors and scores within 1e-4 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+import sfm_oracle as O
+from conftest import load_golden, t, canon_keypoints
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def close(a, b, rtol=RTOL, atol=1e-5):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def sp(sp_weights, dev):
+    from simplesfm_b200.models.superpoint import SuperPoint
+    return lambda **kw: SuperPoint(sp_weights, device=dev, **kw)
+
+
+@pytest.fixture(scope="module")
+def sg(sg_weights, dev):
+    from simplesfm_b200.models.superglue import SuperGlue
+    return lambda **kw: SuperGlue(sg_weights, device=dev, **kw)
+
+
+def test_library_is_native(dev):
+    from simplesfm_b200 import _lib
+    assert _lib.lib().sfm_abi_version() == 1
+    h = _lib.Handle(dev)
+    assert h.h.value
+    h.close()
+
+
+# ------------------------------------------------------------------------------- SuperPoint
+def test_superpoint_stages(sp, dev):
+    g = load_golden("sp_small_stages")
+    m = sp()
+    img = t(g["image"]).to(dev)
+    n, H, W = 1, img.shape[2], img.shape[3]
+    cand, ws = m.detect(img[:, 0].contiguous())
+    h, w = H // 8, W // 8
+    feat = m.tap(n, H, W, 0, ws).view(1, h, w, 128).permute(0, 3, 1, 2)
+    close(feat, g["feat"], 1e-4, 1e-4)
+    logits = m.tap(n, H, W, 1, ws).view(1, h, w, 65).permute(0, 3, 1, 2)
+    close(logits, g["logits"], 1e-4, 1e-4)
+    smap = m.tap(n, H, W, 2, ws).view(1, H, W)
+    close(smap, g["score_map"], 1e-4, 1e-7)
+    dmap = m.tap(n, H, W, 4, ws).view(1, h, w, 256).permute(0, 3, 1, 2)
+    close(torch.nn.functional.normalize(dmap, dim=1), g["dmap"], 1e-4, 1e-5)
+    # NMS of the kernel's own score map must equal the oracle NMS of that same map (exact)
+    nms = m.tap(n, H, W, 3, ws).view(1, H, W)
+    assert torch.equal(nms.cpu(), O.simple_nms(smap.cpu(), 4))
+
+
+def test_simple_nms_exact(dev):
+    from simplesfm_b200.models.superpoint import simple_nms
+    g = load_golden("sp_functions")
+    x = t(g["nms_in"]).to(dev)
+    for r in (4, 2, 0):
+        assert torch.equal(simple_nms(x, r).cpu(), t(g[f"nms_r{r}"])), r
+    # non-tile-aligned, larger radius, against the oracle
+    gen = torch.Generator().manual_seed(3)
+    y = torch.rand(2, 75, 133, generator=gen)
+    for r in (1, 3, 6):
+        assert torch.equal(simple_nms(y.to(dev), r).cpu(), O.simple_nms(y, r)), r
+
+
+def test_sample_descriptors(dev):
+    from simplesfm_b200.models.superpoint import sample_descriptors
+    g = load_golden("sp_functions")
+    out = sample_descriptors(t(g["samp_kpts"])[None].to(dev), t(g["samp_dmap"]).to(dev), 8)
+    close(out[0], g["samp_out"], 1e-4, 1e-6)
+    out_ac = sample_descriptors(t(g["samp_kpts"])[None].to(dev), t(g["samp_dmap"]).to(dev), 8, align_corners=True)
+    close(out_ac[0], O.sample_descriptors(t(g["samp_kpts"]), t(g["samp_dmap"]), 8, True), 1e-4, 1e-6)
+
+
+@pytest.mark.parametrize("tag,mk,masked", [("all", -1, False), ("top200", 200, False), ("masked", -1, True)])
+def test_superpoint_forward(sp, dev, tag, mk, masked):
+    g = load_golden(f"sp_small_{tag}")
+    m = sp(max_keypoints=mk)
+    data = {"image": t(g["image"]).to(dev)}
+    if masked:
+        data["mask"] = t(g["mask"]).to(dev)
+    out = m(data)
+    rk, rs, ro = canon_keypoints(g["keypoints"], g["scores"])
+    ok, os_, oo = canon_keypoints(out["keypoints"].cpu().numpy(), out["scores"].cpu().numpy())
+    assert rk.shape == ok.shape
+    assert np.array_equal(rk, ok)                         # keypoint indices bit-exact
+    close(os_, rs, 1e-4, 0)
+    close(out["descriptors"].cpu().numpy()[:, oo], g["descriptors"][:, ro], 1e-4, 1e-5)
+    s = out["scores"].cpu().numpy()
+    assert np.all(np.diff(s) <= 0)                        # sorted by score descending
+
+
+def test_superpoint_480x640(sp, dev):
+    from simplesfm_b200 import synthetic
+    g = load_golden("sp_480x640_top1024")
+    out = sp(max_keypoints=1024)({"image": synthetic.textured_image(1).to(dev)})
+    assert np.array_equal(out["keypoints"].cpu().numpy(), g["keypoints"])
+    close(out["scores"], g["scores"], 1e-4, 0)
+    close(out["descriptors"][:, :128], g["descriptors_first128"], 1e-4, 1e-5)
+
+
+def test_superpoint_errors(sp_weights, dev):
+    from simplesfm_b200.models.superpoint import SuperPoint
+    from simplesfm_b200._lib import SfmError
+    with pytest.raises(ValueError):
+        SuperPoint(sp_weights, max_keypoints=0, device=dev)
+    with pytest.raises(RuntimeError):
+        SuperPoint({k: v for k, v in sp_weights.items() if k != "conv1a.bias"}, device=dev)
+    m = SuperPoint(sp_weights, device=dev)
+    with pytest.raises(SfmError):
+        m({"image": torch.zeros(1, 1, 64, 64)})           # CPU tensor: no CPU fallback
+    with pytest.raises(SfmError):
+        m({"image": torch.zeros(1, 1, 60, 64, device=dev)})   # H not a multiple of 8
+    # an image with no detections returns empty tensors
+    out = SuperPoint(sp_weights, device=dev, keypoint_threshold=2.0)({"image": torch.zeros(1, 1, 64, 64, device=dev)})
+    assert out["keypoints"].shape == (0, 2) and out["descriptors"].shape == (256, 0)
+
+
+# ------------------------------------------------------------------------------- SuperGlue
+def _sg_data(g, dev):
+    d = {k: t(g[k]).to(dev) for k in ("descriptors0", "descriptors1", "keypoints0", "keypoints1", "scores0", "scores1")}
+    B = d["keypoints0"].shape[0]
+    d["image0"] = d["image1"] = torch.zeros(B, 1, int(g["image_hw"][0]), int(g["image_hw"][1]), device=dev)
+    return d
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+@pytest.mark.parametrize("iters", [20, 100])
+def test_superglue_forward_golden(sg, dev, mode, iters):
+    g = load_golden(f"sg_b2_{mode}_it{iters}")
+    m = sg(sinkhorn_iterations=iters, match_threshold=0.2, bn_mode=mode)
+    data = _sg_data(g, dev)
+    out = m(data)
+    assert out["matches0"].dtype == torch.int64
+    assert np.array_equal(out["matches0"].cpu().numpy(), g["matches0"])       # bit-exact mutual matches
+    assert np.array_equal(out["matches1"].cpu().numpy(), g["matches1"])
+    close(out["matching_scores0"], g["matching_scores0"], 1e-4, 1e-6)
+    close(out["matching_scores1"], g["matching_scores1"], 1e-4, 1e-6)
+    B, K0, K1 = 2, data["keypoints0"].shape[1], data["keypoints1"].shape[1]
+    ws = m.handle.workspace("sg", 0)
+    scores = m.tap(B, K0, K1, 2, ws).view(B, K0, K1)
+    close(scores, g["scores"], 2e-4, 2e-4)
+    if iters == 20:
+        xk = m.tap(B, K0, K1, 0, ws).view(-1, 256)
+        kenc0 = xk[:B * K0].view(B, K0, 256).permute(0, 2, 1) - data["descriptors0"]
+        close(kenc0, g["kenc_0"], 1e-4, 1e-5)
+
+
+def test_superglue_empty_side(sg, dev):
+    g = load_golden("sg_empty_side")
+    m = sg()
+    out = m({"keypoints0": torch.zeros(1, 8, 2, device=dev), "keypoints1": torch.zeros(1, 0, 2, device=dev),
+             "descriptors0": torch.zeros(1, 256, 8, device=dev), "descriptors1": torch.zeros(1, 256, 0, device=dev)})
+    assert out["matches0"].dtype == torch.int32
+    for k in ("matches0", "matches1", "matching_scores0", "matching_scores1"):
+        assert np.array_equal(out[k].cpu().numpy(), g[k])
+
+
+def test_log_optimal_transport(dev):
+    from simplesfm_b200.models.superglue import log_optimal_transport, normalize_keypoints
+    g = load_golden("sg_functions")
+    sc = t(g["ot_scores"]).to(dev)
+    close(log_optimal_transport(sc, 1.0, 20), g["ot_it20"], 1e-4, 1e-4)
+    close(log_optimal_transport(sc, 1.0, 100), g["ot_it100"], 1e-4, 1e-4)
+    close(log_optimal_transport(sc, torch.tensor(2.5), 5), g["ot_alpha2_it5"], 1e-4, 1e-4)
+    close(normalize_keypoints(t(g["nk_in"]).to(dev), (2, 1, 480, 640)), g["nk_out"], 1e-6, 1e-7)
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_superglue_vs_oracle_ragged(sg, sg_weights, dev, mode):
+    """Seeded inputs at a size the oracle finishes in seconds; K0 != K1, neither a multiple of 4."""
+    from simplesfm_b200 import synthetic
+    B, K0, K1 = 3, 333, 251
+    fr = synthetic.feature_scene(2 * B, 333, seed=5)
+    data = {"descriptors0": torch.stack([fr[i][0][:, :K0] for i in range(B)]),
+            "descriptors1": torch.stack([fr[B + i][0][:, :K1] for i in range(B)]),
+            "keypoints0": torch.stack([fr[i][1][:K0] for i in range(B)]),
+            "keypoints1": torch.stack([fr[B + i][1][:K1] for i in range(B)]),
+            "scores0": torch.stack([fr[i][2][:K0] for i in range(B)]),
+            "scores1": torch.stack([fr[B + i][2][:K1] for i in range(B)]),
+            "image0": torch.zeros(B, 1, 480, 640), "image1": torch.zeros(B, 1, 480, 640)}
+    tr = {}
+    ref = O.superglue_forward(sg_weights, data, 20, 0.2, mode, trace=tr)
+    m = sg(sinkhorn_iterations=20, match_threshold=0.2, bn_mode=mode)
+    out = m({k: v.to(dev) for k, v in data.items()})
+    ws = m.handle.workspace("sg", 0)
+    close(m.tap(B, K0, K1, 2, ws).view(B, K0, K1), tr["scores"], 5e-4, 5e-4)
+    a, b = out["matches0"].cpu().numpy(), ref["matches0"].numpy()
+    if not np.array_equal(a, b):
+        # any disagreement must be a numerical near-tie of the top-2 assignment scores
+        bad = np.argwhere(a != b)
+        Z = tr["Z"][:, :-1, :-1]
+        for bi, i in bad:
+            top2 = torch.topk(Z[bi, i], 2).values
+            assert float(top2[0] - top2[1]) < 1e-4 or abs(float(top2[0].exp()) - 0.2) < 1e-4, (bi, i)
+        assert len(bad) <= 2
+    close(out["matching_scores0"], ref["matching_scores0"], 1e-3, 1e-5)
+    assert np.array_equal(out["matches1"].cpu().numpy(), ref["matches1"].numpy()) or not np.array_equal(a, b)
+
+
+def test_sinkhorn_match_properties_full_size(dev):
+    """BASELINE config-5 shape family at a full-size keypoint count (2048): size-independent checks."""
+    from simplesfm_b200 import _lib
+    L = _lib.lib()
+    B, N, M = 2, 2048, 2048
+    g = torch.Generator(device="cpu").manual_seed(1)
+    S = (torch.randn(B, N, M, generator=g) * 2).to(dev)
+    perm = torch.randperm(M, generator=g)[:1200]
+    S[0, torch.arange(1200), perm] += 25.0                 # planted confident matches
+    ws = torch.empty(L.sfm_sinkhorn_workspace_bytes(B, N, M), dtype=torch.uint8, device=dev)
+    Z = torch.empty(B, N + 1, M + 1, device=dev)
+    _lib.check(L.sfm_log_optimal_transport(S.data_ptr(), B, N, M, 1.0, 50, Z.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           torch.cuda.current_stream().cuda_stream))
+    # column marginals are exact after the last (column) update: sum_i exp(Z_ij) = 1 for j < M, N for the bin
+    col = torch.logsumexp(Z, dim=1).exp()
+    close(col[:, :M], torch.ones(B, M), 1e-3, 1e-3)
+    close(col[:, M], torch.full((B,), float(N)), 1e-3, 1e-3)
+    m0 = torch.empty(B, N, dtype=torch.int64, device=dev)
+    m1 = torch.empty(B, M, dtype=torch.int64, device=dev)
+    s0 = torch.empty(B, N, device=dev)
+    s1 = torch.empty(B, M, device=dev)
+    _lib.check(L.sfm_sinkhorn_match(S.data_ptr(), B, N, M, 1.0, 50, 0.2, m0.data_ptr(), m1.data_ptr(), s0.data_ptr(),
+                                    s1.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+    m0c, m1c = m0.cpu(), m1.cpu()
+    assert torch.equal(m0c[0, :1200], perm)                # planted matches recovered
+    for b in range(B):                                     # mutual consistency
+        v = m0c[b] > -1
+        assert torch.equal(m1c[b][m0c[b][v]], torch.nonzero(v)[:, 0])
+    # and the matches equal the argmax structure of the materialised Z (same kernel family, exact)
+    ref = O.mutual_matches(Z.cpu(), 0.2)
+    assert torch.equal(ref["matches0"], m0c) and torch.equal(ref["matches1"], m1c)
+
+
+# ------------------------------------------------------------------------------- Matcher
+def _frames(g, n, dev):
+    from simplesfm_b200.matchers.matcher import Frame
+    return [Frame(t(g[f"desc_{i}"]).to(dev), t(g[f"kpts_{i}"]).to(dev), t(g[f"scores_{i}"]).to(dev),
+                  torch.zeros(1, 480, 640, device=dev)) for i in range(n)]
+
+
+@pytest.mark.parametrize("batch", [4, 1])
+def test_matcher_tables_golden(sp_weights, sg_weights_outdoor, dev, batch):
+    from simplesfm_b200.matchers import Matcher
+    g = load_golden("matcher_4frames")
+    m = Matcher(sp_weights, 4, 0.005, matcher_type="super_glue", super_glue_weights_path=sg_weights_outdoor,
+                match_threshold=0.2, sinkhorn_iterations=20, super_glue_batch=batch, device=dev)
+    names = {i + 1: f"img_{i:03d}.png" for i in range(4)}
+    frames, table, names_out = m.match_frames(_frames(g, 4, dev), names, lambda p: True)
+    assert len(table) == 6 and names_out is names
+    for (a, b), tab in table.items():
+        ref = g[f"sg_b{batch}_{int(a)}_{int(b)}"]
+        assert tab.dtype == np.uint32 and isinstance(a, np.integer)
+        assert np.array_equal(tab, ref), (a, b)
+    _, table, _ = m.match_frames(_frames(g, 4, dev), names, lambda p: abs(p[0] - p[1]) <= 2)
+    assert np.array_equal(np.array(sorted((int(a), int(b)) for a, b in table)), g["sg_filtered_keys"])
+
+
+def test_simple_matcher_golden(sp_weights, dev):
+    from simplesfm_b200.matchers import Matcher
+    from simplesfm_b200.matchers.simple_matcher import SimpleMatcher
+    g = load_golden("matcher_4frames")
+    frames = _frames(g, 4, dev)
+    sm = SimpleMatcher(0.7)
+    out = sm.match_two_way_cuda(frames[0].descriptors, frames[1].descriptors)
+    close(out, g["simple_two_way_cuda"], 1e-4, 1e-5)
+    close(sm.match_two_way(frames[0].descriptors, frames[1].descriptors), g["simple_two_way_np"], 1e-4, 1e-5)
+    m = Matcher(sp_weights, 4, 0.005, matcher_type="simple", match_threshold=0.7, device=dev)
+    _, table, _ = m.match_frames(frames, {i + 1: str(i) for i in range(4)}, lambda p: True)
+    for (a, b), tab in table.items():
+        assert np.array_equal(tab, g[f"simple_{int(a)}_{int(b)}"])
+    assert sm.match_two_way_cuda(frames[0].descriptors[:, :0], frames[1].descriptors).shape == (3, 0)
+    with pytest.raises(ValueError):
+        sm.match_two_way_cuda(frames[0].descriptors, frames[1].descriptors, -1.0)
+
+
+def test_matcher_images_e2e_golden(sp_weights, sg_weights_outdoor, dev):
+    """images -> SuperPoint -> SuperGlue -> tables, against the reference Matcher run on CPU."""
+    from simplesfm_b200.matchers import Matcher
+    from simplesfm_b200.matchers.matcher import Frame
+    g = load_golden("matcher_images_e2e")
+    m = Matcher(sp_weights, 4, 0.005, matcher_type="super_glue", super_glue_weights_path=sg_weights_outdoor,
+                match_threshold=0.2, sinkhorn_iterations=20, super_glue_batch=2, device=dev)
+    frames = []
+    for i in range(3):
+        im = t(g[f"image_{i}"]).to(dev)
+        r = m.super_point_extractor({"image": im})
+        assert np.array_equal(r["keypoints"].cpu().numpy(), g[f"kpts_{i}"])
+        frames.append(Frame(r["descriptors"], r["keypoints"], r["scores"], im[0]))
+    _, table, _ = m.match_frames(frames, {1: "a", 2: "b", 3: "c"}, None if False else (lambda p: True))
+    for (a, b), tab in table.items():
+        assert np.array_equal(tab, g[f"table_{int(a)}_{int(b)}"]), (a, b)
