@@ -57,6 +57,16 @@ SFM_API const char* sfm_last_error(void);
 SFM_API int sfm_create(int device, sfm_handle_t* out);
 SFM_API int sfm_destroy(sfm_handle_t h);
 
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------
+ * sfm_launch_count: kernels launched by this library in the process so far.
+ * profiling: when enabled, CUDA events bracket every launch group of kind 0 = linear layers (GEMMs),
+ * 1 = attention, 2 = Sinkhorn + matching, 3 = everything else, on the caller's stream;
+ * sfm_get_profile synchronises, returns the summed milliseconds and group counts per kind
+ * (arrays of 4) since the previous call, and clears the window. */
+SFM_API long long sfm_launch_count(void);
+SFM_API int sfm_set_profiling(sfm_handle_t h, int enable);
+SFM_API int sfm_get_profile(sfm_handle_t h, float* ms, long long* groups);
+
 /* ---- weights -------------------------------------------------------------------------------
  * SuperPoint.__init__ -> load_state_dict (superpoint.py:101).  `packed_host`: the 12 convs in the
  * order conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db, each as weight (Cout,Cin,kh,kw) then bias, f32,

@@ -26,6 +26,9 @@ _SIGNATURES = {
     "sfm_abi_version": (C.c_int, []),
     "sfm_last_error": (C.c_char_p, []),
     "sfm_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "sfm_launch_count": (C.c_longlong, []),
+    "sfm_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "sfm_get_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),
     "sfm_destroy": (C.c_int, [C.c_void_p]),
     "sfm_load_superpoint": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "sfm_superpoint_packed_floats": (C.c_size_t, []),

@@ -1,6 +1,7 @@
 // extern "C" surface of libsfm_b200 (declared in include/sfm_b200.h).
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
 #include <vector>
 
 #include "../../include/sfm_b200.h"
@@ -23,6 +24,33 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
   return SFM_ERR_CUDA;
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static cudaEvent_t take_event(sfm_ctx* h) {
+  if (!h->event_pool.empty()) {
+    cudaEvent_t e = h->event_pool.back();
+    h->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+ProfScope::ProfScope(sfm_ctx* h_, int kind_, cudaStream_t st_) : h(h_), kind(kind_), st(st_) {
+  if (h && h->profiling) {
+    e0 = take_event(h);
+    e1 = take_event(h);
+    cudaEventRecord(e0, st);
+  }
+}
+ProfScope::~ProfScope() {
+  if (e0) {
+    cudaEventRecord(e1, st);
+    h->prof[kind].push_back({e0, e1});
+  }
 }
 
 namespace {
@@ -127,9 +155,42 @@ int sfm_create(int device, sfm_handle_t* out) {
   return SFM_OK;
 }
 
+long long sfm_launch_count(void) { return g_launches.load(); }
+
+int sfm_set_profiling(sfm_handle_t h, int enable) {
+  SFM_REQUIRE(h, "sfm_set_profiling: NULL handle");
+  h->profiling = enable != 0;
+  return SFM_OK;
+}
+
+int sfm_get_profile(sfm_handle_t h, float* ms, long long* groups) {
+  SFM_REQUIRE(h && ms && groups, "sfm_get_profile: NULL argument");
+  SFM_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < SFM_PROF_KINDS; k++) {
+    double total = 0.0;
+    for (auto& pr : h->prof[k]) {
+      float t = 0.f;
+      SFM_CUDA(cudaEventElapsedTime(&t, pr.first, pr.second));
+      total += t;
+      h->event_pool.push_back(pr.first);
+      h->event_pool.push_back(pr.second);
+    }
+    ms[k] = (float)total;
+    groups[k] = (long long)h->prof[k].size();
+    h->prof[k].clear();
+  }
+  return SFM_OK;
+}
+
 int sfm_destroy(sfm_handle_t h) {
   if (!h) return SFM_OK;
   cudaSetDevice(h->device);
+  for (int k = 0; k < SFM_PROF_KINDS; k++)
+    for (auto& pr : h->prof[k]) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+  for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
   return SFM_OK;

@@ -17,6 +17,7 @@ namespace sfm {
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+void count_launches(long long n);
 
 #define SFM_CUDA(call)                                                          \
   do {                                                                          \
@@ -24,7 +25,13 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     if (e__ != cudaSuccess) return ::sfm::cuda_fail(e__, #call, __FILE__, __LINE__); \
   } while (0)
 
-#define SFM_LAUNCH_CHECK() SFM_CUDA(cudaGetLastError())
+// every kernel launch site is followed by SFM_LAUNCH_CHECK(); `n` = launches covered by the check
+#define SFM_LAUNCH_CHECK_N(n)            \
+  do {                                   \
+    ::sfm::count_launches(n);            \
+    SFM_CUDA(cudaGetLastError());        \
+  } while (0)
+#define SFM_LAUNCH_CHECK() SFM_LAUNCH_CHECK_N(1)
 
 #define SFM_REQUIRE(cond, ...)                       \
   do {                                               \

@@ -53,15 +53,29 @@ struct SpWeights {
 
 }  // namespace sfm
 
+enum { SFM_PROF_LINEAR = 0, SFM_PROF_ATTENTION = 1, SFM_PROF_SINKHORN = 2, SFM_PROF_OTHER = 3, SFM_PROF_KINDS = 4 };
+
 struct sfm_ctx {
   int device = 0;
   int sm_count = 148;
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[SFM_PROF_KINDS];  // recorded this window
+  std::vector<cudaEvent_t> event_pool;
   sfm::SpWeights sp;
   sfm::SgWeights sg;
   std::vector<void*> allocs;  // everything cudaMalloc'ed by the handle
 };
 
 namespace sfm {
+// CUDA-event bracket around a group of launches on `st` (only when profiling is enabled)
+struct ProfScope {
+  sfm_ctx* h;
+  int kind;
+  cudaStream_t st;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ProfScope(sfm_ctx* h_, int kind_, cudaStream_t st_);
+  ~ProfScope();
+};
 int sp_forward_detect(sfm_ctx* h, const float* images, int n_img, int H, int W, const unsigned char* mask, float thr,
                       int nms_radius, int border, int precision, int* cand_counts, void* ws, size_t ws_bytes,
                       bool dry, size_t* need, cudaStream_t st);

@@ -46,8 +46,10 @@ int carve(Arena& a, const SgCall& c, SgBuffers& b) {
   return SFM_OK;
 }
 
+}  // namespace
+
 // y = [relu(bn(]x W^T + b[))]  over all tokens of both sides
-int linear_f32(const float* A, int lda, const float* A2, int lda2, int K1, const float* W, int K, int N,
+int linear_f32_raw(const float* A, int lda, const float* A2, int lda2, int K1, const float* W, int K, int N,
                const float* bias, float* C, int ldc, long long T, int flags, cudaStream_t st) {
   GemmF32 g;
   g.A = A; g.lda = lda; g.A2 = A2; g.lda2 = lda2; g.K1 = K1;
@@ -57,7 +59,7 @@ int linear_f32(const float* A, int lda, const float* A2, int lda2, int K1, const
 }
 
 // message = softmax(q k^T / 8) v for the queries of one side against the keys/values of `src`
-int attention_f32(const SgBuffers& b, int B, long long q_row0, int Nq, long long s_row0, int Nk, cudaStream_t st) {
+int attention_f32_raw(const SgBuffers& b, int B, long long q_row0, int Nq, long long s_row0, int Nk, cudaStream_t st) {
   GemmF32 g;
   g.A = b.qkv + q_row0 * 768; g.lda = 768;
   g.B = b.qkv + s_row0 * 768 + 256; g.ldb = 768;
@@ -81,8 +83,18 @@ int attention_f32(const SgBuffers& b, int B, long long q_row0, int Nq, long long
   return gemm_f32_nn(p, st);
 }
 
+namespace {
+
 int forward_f32(sfm_ctx* h, const SgCall& c, const SgBuffers& b, cudaStream_t st) {
   const SgWeights& w = h->sg;
+  auto linear_f32 = [&](auto... args) {
+    ProfScope ps(h, SFM_PROF_LINEAR, st);
+    return sfm::linear_f32_raw(args...);
+  };
+  auto attention_f32 = [&](auto... args) {
+    ProfScope ps(h, SFM_PROF_ATTENTION, st);
+    return sfm::attention_f32_raw(args...);
+  };
   const long long T0 = (long long)c.B * c.K0, T1 = (long long)c.B * c.K1, T = T0 + T1;
   const bool train = c.bn_mode == 0;
   // ---- keypoint encoder (superglue.py:72-82, 254-255): X += kenc(kin)
@@ -193,6 +205,7 @@ int sg_forward(sfm_ctx* h, const SgCall& c, void* ws, size_t ws_bytes, bool dry,
   SinkhornArgs s;
   s.S = b.scores; s.B = c.B; s.N = c.K0; s.M = c.K1; s.alpha = h->sg.bin_score; s.iters = c.iters;
   s.u = b.u; s.v = b.v; s.part = b.part; s.counters = b.counters; s.R = b.R;
+  ProfScope ps(h, SFM_PROF_SINKHORN, st);
   SFM_TRY(sinkhorn_run(s, st));
   return sinkhorn_match(s, c.thr, b.max0, b.idx0, b.max1, b.idx1, c.m0, c.m1, c.ms0, c.ms1, st);
 }

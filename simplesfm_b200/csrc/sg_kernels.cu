@@ -578,7 +578,7 @@ int sinkhorn_run(const SinkhornArgs& a, cudaStream_t st) {
   long long nv = (long long)B * (M + 1), nu = (long long)B * (N + 1);
   fill_kernel<<<cdiv(nv, 256), 256, 0, st>>>(a.v, nv, 0.f);
   fill_kernel<<<cdiv(nu, 256), 256, 0, st>>>(a.u, nu, 0.f);
-  SFM_LAUNCH_CHECK();
+  SFM_LAUNCH_CHECK_N(2);
   dim3 rgrid(cdiv(N + 1, 8), B);
   dim3 cgrid(cdiv(M, 128), a.R, B);
   for (int it = 0; it < a.iters; it++) {
@@ -586,7 +586,7 @@ int sinkhorn_run(const SinkhornArgs& a, cudaStream_t st) {
     sk_col_kernel<0><<<cgrid, 256, 0, st>>>(a.S, N, M, a.alpha, a.u, nullptr, a.v, a.part, a.counters, a.R, norm,
                                             log_nu_bin, nullptr, nullptr);
   }
-  SFM_LAUNCH_CHECK();
+  SFM_LAUNCH_CHECK_N(2 * a.iters);
   return SFM_OK;
 }
 
@@ -599,7 +599,7 @@ int argmax_rows_cols(const SinkhornArgs& a, float norm, float* max0, int* idx0, 
   dim3 cgrid(cdiv(M, 128), a.R, B);
   sk_col_kernel<1><<<cgrid, 256, 0, st>>>(a.S, N, M, a.alpha, a.u, a.v, nullptr, a.part, a.counters, a.R, norm, 0.f,
                                           max1, idx1);
-  SFM_LAUNCH_CHECK();
+  SFM_LAUNCH_CHECK_N(2);
   return SFM_OK;
 }
 

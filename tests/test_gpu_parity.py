@@ -114,9 +114,19 @@ def test_superpoint_480x640(sp, dev):
     from simplesfm_b200 import synthetic
     g = load_golden("sp_480x640_top1024")
     out = sp(max_keypoints=1024)({"image": synthetic.textured_image(1).to(dev)})
-    assert np.array_equal(out["keypoints"].cpu().numpy(), g["keypoints"])
-    close(out["scores"], g["scores"], 1e-4, 0)
-    close(out["descriptors"][:, :128], g["descriptors_first128"], 1e-4, 1e-5)
+    kp, ref = out["keypoints"].cpu().numpy(), g["keypoints"]
+    sc, rsc = out["scores"].cpu().numpy(), g["scores"]
+    close(sc, rsc, 1e-4, 0)
+    same = np.all(kp == ref, axis=1)
+    print(f"480x640: {same.sum()}/1024 keypoints at identical rank")
+    # the keypoint SET must be identical; a rank may differ only between scores that agree to
+    # float32 rounding (the reference leaves the order of such near-ties to torch.argsort)
+    assert {tuple(r) for r in kp.tolist()} == {tuple(r) for r in ref.tolist()}
+    for i in np.nonzero(~same)[0]:
+        j = int(np.nonzero(np.all(ref == kp[i], axis=1))[0][0])
+        assert abs(rsc[j] - rsc[i]) <= 2e-6 * rsc[i], (i, j, rsc[i], rsc[j])
+    idx = [int(np.nonzero(np.all(kp == ref[j], axis=1))[0][0]) for j in range(128)]
+    close(out["descriptors"][:, idx], g["descriptors_first128"], 1e-4, 1e-5)
 
 
 def test_superpoint_errors(sp_weights, dev):
@@ -300,12 +310,20 @@ def test_matcher_images_e2e_golden(sp_weights, sg_weights_outdoor, dev):
     g = load_golden("matcher_images_e2e")
     m = Matcher(sp_weights, 4, 0.005, matcher_type="super_glue", super_glue_weights_path=sg_weights_outdoor,
                 match_threshold=0.2, sinkhorn_iterations=20, super_glue_batch=2, device=dev)
-    frames = []
+    frames, kps = [], []
     for i in range(3):
         im = t(g[f"image_{i}"]).to(dev)
         r = m.super_point_extractor({"image": im})
-        assert np.array_equal(r["keypoints"].cpu().numpy(), g[f"kpts_{i}"])
+        kp = r["keypoints"].cpu().numpy()
+        # identical keypoint set; rank may differ only between float32-rounding near-ties
+        assert {tuple(x) for x in kp.tolist()} == {tuple(x) for x in g[f"kpts_{i}"].tolist()}
+        close(r["scores"], g[f"scores_{i}"], 1e-4, 0)
+        kps.append(kp)
         frames.append(Frame(r["descriptors"], r["keypoints"], r["scores"], im[0]))
-    _, table, _ = m.match_frames(frames, {1: "a", 2: "b", 3: "c"}, None if False else (lambda p: True))
+    _, table, _ = m.match_frames(frames, {1: "a", 2: "b", 3: "c"}, lambda p: True)
+    # compare matches by keypoint coordinates (index order can differ at near-tie ranks)
     for (a, b), tab in table.items():
-        assert np.array_equal(tab, g[f"table_{int(a)}_{int(b)}"]), (a, b)
+        ref = g[f"table_{int(a)}_{int(b)}"]
+        got = {(tuple(kps[a - 1][i]), tuple(kps[b - 1][j])) for i, j in tab.tolist()}
+        want = {(tuple(g[f"kpts_{a - 1}"][i]), tuple(g[f"kpts_{b - 1}"][j])) for i, j in ref.tolist()}
+        assert got == want, (a, b, len(got ^ want))
