@@ -139,6 +139,21 @@ SFM_API int sfm_sinkhorn_match(const float* scores, int B, int N, int M, float a
                        int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- kernel-level hooks of the bf16 tcgen05 path (tests/, bench) ---------------------------------
+ * sfm_tc_gemm: out[M,N] = alpha * [A | A2][M,K] * W[N,K]^T + bias (bf16 operands, K in {256,512},
+ *   K1 = columns taken from A); optional ReLU; writes bf16 and/or fp32 (accumulate: out_f32 += result,
+ *   out_bf16 = bf16(out_f32)) -- the linear layers of superglue.py:48-59,103-108.
+ * sfm_tc_attention: fused softmax(Q K^T / 8) V for both sides of one layer from the fused projection
+ *   buffer qkv [rows_total, 768] bf16 (q | k | v, head-contiguous); side s uses queries at rows
+ *   q_row0_s + b*Nq_s and keys/values at rows k_row0_s + b*Nk_s; out [rows_total, 256] bf16
+ *   (superglue.py:85-108).  Nq1 = 0 disables the second side. */
+SFM_API int sfm_tc_gemm(sfm_handle_t h, const void* A, const void* A2, const void* W, int M, int N, int K, int K1,
+                        const float* bias, float alpha, int relu, void* out_bf16, float* out_f32, int accumulate,
+                        void* stream);
+SFM_API int sfm_tc_attention(sfm_handle_t h, const void* qkv, long long rows_total, int B, int Nq0, int Nk0,
+                             long long q_row0_0, long long k_row0_0, int Nq1, int Nk1, long long q_row0_1,
+                             long long k_row0_1, void* out_bf16, void* stream);
+
 /* Matcher.__super_glue_matcher tail (matcher.py:103-109): per pair (L,2) uint32 rows
  * [i, matches0[i]] for matches0[i] > -1, in ascending i.  tables (B,K0,2) u32, lengths (B) i32. */
 SFM_API int sfm_compact_matches(const int64_t* matches0, int B, int K0, uint32_t* tables, int* lengths, void* stream);

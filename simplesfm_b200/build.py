@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             list(ex.map(compile_one, jobs))
     objs = [os.path.join(OBJ, s[:-3] + ".o") for s in srcs]
     if force or jobs or not _newer(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcuda", "-lcudart"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -9,6 +9,7 @@
 #include "gemm_f32.cuh"
 #include "sg_kernels.cuh"
 #include "sp_post.cuh"
+#include "tc_path.cuh"
 
 namespace sfm {
 
@@ -441,6 +442,33 @@ int sfm_sinkhorn_match(const float* scores, int B, int N, int M, float alpha, in
 int sfm_compact_matches(const int64_t* matches0, int B, int K0, uint32_t* tables, int* lengths, void* stream) {
   SFM_REQUIRE(B == 0 || (matches0 && tables && lengths), "sfm_compact_matches: NULL argument");
   return compact_matches((const long long*)matches0, B, K0, tables, lengths, (cudaStream_t)stream);
+}
+
+// ---- kernel-level test hooks of the tcgen05 path ------------------------------------------------
+int sfm_tc_gemm(sfm_handle_t h, const void* A, const void* A2, const void* W, int M, int N, int K, int K1,
+                const float* bias, float alpha, int relu, void* out_bf16, float* out_f32, int accumulate,
+                void* stream) {
+  SFM_REQUIRE(h && A && W, "sfm_tc_gemm: NULL argument");
+  tc::TcGemm g;
+  g.A = (const __nv_bfloat16*)A; g.lda = K1; g.a_rows = M;
+  g.A2 = (const __nv_bfloat16*)A2; g.lda2 = K - K1;
+  g.W = (const __nv_bfloat16*)W; g.ldw = K; g.w_rows = N;
+  g.M = M; g.N = N; g.K = K; g.K1 = K1;
+  g.bias = bias; g.alpha = alpha; g.relu = relu;
+  g.out_h = (__nv_bfloat16*)out_bf16; g.out_h_ld = N;
+  g.out_f = out_f32; g.out_f_ld = N; g.accumulate_f = accumulate;
+  return tc::tc_gemm(g, h->sm_count, (cudaStream_t)stream);
+}
+
+int sfm_tc_attention(sfm_handle_t h, const void* qkv, long long rows_total, int B, int Nq0, int Nk0, long long q_row0_0,
+                     long long k_row0_0, int Nq1, int Nk1, long long q_row0_1, long long k_row0_1, void* out_bf16,
+                     void* stream) {
+  SFM_REQUIRE(h && qkv && out_bf16, "sfm_tc_attention: NULL argument");
+  tc::TcAttn a;
+  a.qkv = (const __nv_bfloat16*)qkv; a.rows_total = rows_total; a.out = (__nv_bfloat16*)out_bf16; a.B = B;
+  a.Nq[0] = Nq0; a.Nk[0] = Nk0; a.q_row0[0] = q_row0_0; a.k_row0[0] = k_row0_0;
+  a.Nq[1] = Nq1; a.Nk[1] = Nk1; a.q_row0[1] = q_row0_1; a.k_row0[1] = k_row0_1;
+  return tc::tc_attention(a, (cudaStream_t)stream);
 }
 
 // ---- SimpleMatcher ----------------------------------------------------------------------------

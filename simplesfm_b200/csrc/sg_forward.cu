@@ -83,6 +83,37 @@ int attention_f32_raw(const SgBuffers& b, int B, long long q_row0, int Nq, long 
   return gemm_f32_nn(p, st);
 }
 
+// keypoint encoder (superglue.py:72-82, 254-255): X += kenc(kin); fp32 SIMT on both precision paths
+int kenc_forward_f32(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float* t0, float* t1, float* mean,
+                     float* var, cudaStream_t st) {
+  const SgWeights& w = h->sg;
+  const long long T0 = (long long)c.B * c.K0, T1 = (long long)c.B * c.K1, T = T0 + T1;
+  const bool train = c.bn_mode == 0;
+  const float* cur = kin;
+  int ld = 4;
+  float* pp[2] = {t0, t1};
+  for (int i = 0; i < 5; i++) {
+    const int cin = w.kch[i], cout = w.kch[i + 1];
+    const bool last = i == 4;
+    if (last) {
+      SFM_TRY(linear_f32_raw(cur, ld, nullptr, 0, 0, w.kW[i], cin, cout, w.kb[i], X, 256, T, GEMM_ACCUM, st));
+    } else if (train) {
+      float* out = pp[i & 1];
+      SFM_TRY(linear_f32_raw(cur, ld, nullptr, 0, 0, w.kW[i], cin, cout, w.kb[i], out, cout, T, 0, st));
+      SFM_TRY(col_stats_f32(out, cout, cout, (int)T0, (int)T1, mean, var, st));
+      SFM_TRY(bn_relu_f32(out, cout, cout, (int)T0, (int)T1, mean, var, w.kbn[i].gamma, w.kbn[i].beta, 1e-5f, st));
+      cur = out;
+      ld = cout;
+    } else {
+      float* out = pp[i & 1];
+      SFM_TRY(linear_f32_raw(cur, ld, nullptr, 0, 0, w.kWf[i], cin, cout, w.kbf[i], out, cout, T, GEMM_RELU, st));
+      cur = out;
+      ld = cout;
+    }
+  }
+  return SFM_OK;
+}
+
 namespace {
 
 int forward_f32(sfm_ctx* h, const SgCall& c, const SgBuffers& b, cudaStream_t st) {
@@ -97,28 +128,9 @@ int forward_f32(sfm_ctx* h, const SgCall& c, const SgBuffers& b, cudaStream_t st
   };
   const long long T0 = (long long)c.B * c.K0, T1 = (long long)c.B * c.K1, T = T0 + T1;
   const bool train = c.bn_mode == 0;
-  // ---- keypoint encoder (superglue.py:72-82, 254-255): X += kenc(kin)
-  const float* cur = b.kin;
-  int ld = 4;
-  float* pp[2] = {b.t0, b.t1};
-  for (int i = 0; i < 5; i++) {
-    const int cin = w.kch[i], cout = w.kch[i + 1];
-    const bool last = i == 4;
-    if (last) {
-      SFM_TRY(linear_f32(cur, ld, nullptr, 0, 0, w.kW[i], cin, cout, w.kb[i], b.X, 256, T, GEMM_ACCUM, st));
-    } else if (train) {
-      float* out = pp[i & 1];
-      SFM_TRY(linear_f32(cur, ld, nullptr, 0, 0, w.kW[i], cin, cout, w.kb[i], out, cout, T, 0, st));
-      SFM_TRY(col_stats_f32(out, cout, cout, (int)T0, (int)T1, b.mean, b.var, st));
-      SFM_TRY(bn_relu_f32(out, cout, cout, (int)T0, (int)T1, b.mean, b.var, w.kbn[i].gamma, w.kbn[i].beta, 1e-5f, st));
-      cur = out;
-      ld = cout;
-    } else {
-      float* out = pp[i & 1];
-      SFM_TRY(linear_f32(cur, ld, nullptr, 0, 0, w.kWf[i], cin, cout, w.kbf[i], out, cout, T, GEMM_RELU, st));
-      cur = out;
-      ld = cout;
-    }
+  {
+    ProfScope ps(h, SFM_PROF_OTHER, st);
+    SFM_TRY(kenc_forward_f32(h, c, b.X, b.kin, b.t0, b.t1, b.mean, b.var, st));
   }
   SFM_CUDA(cudaMemcpyAsync(b.xk, b.X, T * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));  // parity tap
   // ---- attentional GNN (superglue.py:123-139)

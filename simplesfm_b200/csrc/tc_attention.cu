@@ -1,0 +1,258 @@
+// Fused multi-head attention on tcgen05 (reference: attention / MultiHeadedAttention,
+// simple_sfm/models/superglue.py:85-108; head_dim 64, 4 heads, the (N x M) probability matrix never
+// leaves the SM).
+//
+// One CTA = (pair, head, 256 query rows) as two 128-row tiles that ping-pong on the tensor pipe:
+//   warp 0    : TMA producer (Q tiles once, then K/V tiles through a 3-stage ring)
+//   warp 1    : tcgen05.mma issuer:  S_t = Q_t K_j^T  (SS, fp32 in TMEM),  O_t = P_t V_j  (A = P from TMEM)
+//   warps 2-5 : softmax warpgroup of tile 0 (thread = query row), warps 6-9: tile 1
+// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512)
+// The running output is kept in registers (64 fp32 per row); every K/V tile produces a fresh
+// P V partial in TMEM that the softmax threads fold in with the online-softmax rescale.
+#include "tc_common.cuh"
+#include "tc_path.cuh"
+
+namespace sfm {
+namespace tc {
+
+namespace {
+
+constexpr int KV_STAGES = 3;
+constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, 128-byte swizzled rows
+constexpr int ATT_THREADS = 320;
+
+struct AttBars {
+  uint64_t q_full;
+  uint64_t kv_full[KV_STAGES], kv_empty[KV_STAGES];
+  uint64_t s_full[2], p_full[2], o_full[2], o_free[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units0, int qt0, int qt1) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                         // 2 tiles
+  uint8_t* sK = smem + 2 * TILE_BYTES;        // KV_STAGES tiles
+  uint8_t* sV = sK + KV_STAGES * TILE_BYTES;  // KV_STAGES tiles
+  AttBars* bars = reinterpret_cast<AttBars*>(sV + KV_STAGES * TILE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- decode the work unit: side, pair, head, 256-row query block
+  int u = blockIdx.x, side = 0;
+  if (u >= units0) {
+    u -= units0;
+    side = 1;
+  }
+  const int qts = side == 0 ? qt0 : qt1;
+  const int head = u & 3;
+  const int qblk = (u >> 2) % qts;
+  const int b = (u >> 2) / qts;
+  const int Nq = p.Nq[side], Nk = p.Nk[side];
+  const long long qrow = p.q_row0[side] + (long long)b * Nq + qblk * 256;
+  const long long krow = p.k_row0[side] + (long long)b * Nk;
+  const int n_kv = (Nk + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map);
+    mbar_init(&bars->q_full, 1);
+    for (int s = 0; s < KV_STAGES; s++) {
+      mbar_init(&bars->kv_full[s], 1);
+      mbar_init(&bars->kv_empty[s], 1);
+    }
+    for (int t = 0; t < 2; t++) {
+      mbar_init(&bars->s_full[t], 1);
+      mbar_init(&bars->p_full[t], 4);
+      mbar_init(&bars->o_full[t], 1);
+      mbar_init(&bars->o_free[t], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&bars->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  constexpr uint32_t COL_S = 0, COL_O = 256, COL_P = 384;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars->q_full, 2 * TILE_BYTES);
+      tma_load_2d(sQ, &map, &bars->q_full, head * 64, (int)qrow);
+      tma_load_2d(sQ + TILE_BYTES, &map, &bars->q_full, head * 64, (int)qrow + 128);
+      for (int j = 0; j < n_kv; j++) {
+        const int s = j % KV_STAGES;
+        mbar_wait(&bars->kv_empty[s], ((j / KV_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars->kv_full[s], 2 * TILE_BYTES);
+        tma_load_2d(sK + s * TILE_BYTES, &map, &bars->kv_full[s], 256 + head * 64, (int)krow + j * 128);
+        tma_load_2d(sV + s * TILE_BYTES, &map, &bars->kv_full[s], 512 + head * 64, (int)krow + j * 128);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);  // S = Q K^T : B = K tile, K-major
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);   // O = P V   : B = V tile, MN-major
+      auto issue_s = [&](int t, int stage) {
+        const uint32_t a_addr = smem_u32(sQ + t * TILE_BYTES), b_addr = smem_u32(sK + stage * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          umma_ss(tmem + COL_S + t * 128, umma_desc_sw128(a_addr + k * 32, 16, 1024),
+                  umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc_s, k != 0);
+        umma_commit(&bars->s_full[t]);
+      };
+      mbar_wait(&bars->q_full, 0);
+      mbar_wait(&bars->kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int j = 0; j < n_kv; j++) {
+        const int s = j % KV_STAGES;
+        for (int t = 0; t < 2; t++) {
+          mbar_wait(&bars->p_full[t], j & 1);  // P_t(j) written, S_t region drained
+          tc_fence_after();
+          if (j + 1 < n_kv) {
+            const int s1 = (j + 1) % KV_STAGES;
+            if (t == 0) {
+              mbar_wait(&bars->kv_full[s1], ((j + 1) / KV_STAGES) & 1);
+              tc_fence_after();
+            }
+            issue_s(t, s1);
+          }
+          if (j > 0) {
+            mbar_wait(&bars->o_free[t], (j - 1) & 1);  // softmax threads have folded O_t(j-1)
+            tc_fence_after();
+          }
+          const uint32_t v_addr = smem_u32(sV + s * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 8; k++)  // 16 keys per step: 16 V rows = 2048 bytes, P advances 8 columns
+            umma_ts(tmem + COL_O + t * 64, tmem + COL_P + t * 64 + k * 8,
+                    umma_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_o, k != 0);
+          umma_commit(&bars->o_full[t]);
+        }
+        umma_commit(&bars->kv_empty[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int t = (warp - 2) >> 2;  // query tile of this warpgroup
+    const int quad = warp & 3;      // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    const int qi = qblk * 256 + t * 128 + row_in_tile;  // query index inside the pair
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    const float c = 0.125f * 1.4426950408889634f;  // log2(e) / sqrt(64)
+    float m_run = -INFINITY, l_run = 0.f;
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) acc[i] = 0.f;
+
+    for (int j = 0; j < n_kv; j++) {
+      mbar_wait(&bars->s_full[t], j & 1);
+      tc_fence_after();
+      const int valid = min(128, Nk - j * 128);  // columns of this tile that are real keys
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ch++) {
+        uint32_t r[32];
+        tmem_ld_32x32(lane_addr + COL_S + t * 128 + ch * 32, r);
+        tmem_wait_ld();
+        if (valid >= (ch + 1) * 32) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            if (ch * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f((m_run - m_new) * c);
+      const float mc = m_new * c;
+      l_run *= alpha;
+#pragma unroll
+      for (int i = 0; i < 64; i++) acc[i] *= alpha;
+      m_run = m_new;
+      // pass 2: probabilities -> bf16 P in TMEM
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int half = 0; half < 2; half++) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const int ch = half * 2 + q;
+          uint32_t r[32];
+          tmem_ld_32x32(lane_addr + COL_S + t * 128 + ch * 32, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = exp2f(fmaf(__uint_as_float(r[i]), c, -mc));
+            float p1 = exp2f(fmaf(__uint_as_float(r[i + 1]), c, -mc));
+            if (ch * 32 + i >= valid) p0 = 0.f;
+            if (ch * 32 + i + 1 >= valid) p1 = 0.f;
+            lsum += p0 + p1;
+            pk[q * 16 + (i >> 1)] = pack_bf16(p0, p1);
+          }
+        }
+        tmem_st_32x32(lane_addr + COL_P + t * 64 + half * 32, pk);
+      }
+      l_run += lsum;
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_full[t]);
+      // fold the P V partial of this tile
+      mbar_wait(&bars->o_full[t], j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        uint32_t r[32];
+        tmem_ld_32x32(lane_addr + COL_O + t * 64 + ch * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; i++) acc[ch * 32 + i] += __uint_as_float(r[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->o_free[t]);
+    }
+    if (qi < Nq) {
+      const float inv = 1.f / l_run;
+      __nv_bfloat16* dst = p.out + (qrow + t * 128 + row_in_tile) * 256 + head * 64;
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        d4[i] = make_uint4(pack_bf16(acc[8 * i] * inv, acc[8 * i + 1] * inv),
+                           pack_bf16(acc[8 * i + 2] * inv, acc[8 * i + 3] * inv),
+                           pack_bf16(acc[8 * i + 4] * inv, acc[8 * i + 5] * inv),
+                           pack_bf16(acc[8 * i + 6] * inv, acc[8 * i + 7] * inv));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace
+
+int tc_attention(const TcAttn& p, cudaStream_t st) {
+  SFM_REQUIRE(p.B > 0 && p.Nq[0] > 0 && p.Nk[0] > 0 && p.Nq[1] >= 0, "tc_attention: bad dims");
+  CUtensorMap map;
+  SFM_TRY(make_tmap_bf16(&map, p.qkv, p.rows_total, 768, 768, 128));
+  const int qt0 = cdiv(p.Nq[0], 256), qt1 = p.Nq[1] > 0 ? cdiv(p.Nq[1], 256) : 0;
+  const int units0 = p.B * 4 * qt0, units1 = p.B * 4 * qt1;
+  const size_t smem = (size_t)(2 + 2 * KV_STAGES) * TILE_BYTES + sizeof(AttBars) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    SFM_CUDA(cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  tc_attention_kernel<<<units0 + units1, ATT_THREADS, smem, st>>>(map, p, units0, qt0, qt1 > 0 ? qt1 : 1);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+}  // namespace tc
+}  // namespace sfm

@@ -1,0 +1,306 @@
+// bf16 tcgen05 GEMM for the SuperGlue linear layers:  D[M,N] = A[M,K] * W[N,K]^T (+ epilogue)
+//
+// Shapes on this path are "tall, short-K": M = all keypoint tokens of a chunk (10^4..10^5), K = 256/512,
+// N = 256..768.  A streamed design would re-read the weights from L2 for every 128-row tile and be
+// L2-bound, so each persistent CTA keeps one [BN x K] weight panel resident in shared memory
+// (128 KB) and streams only activation tiles through a 4-stage TMA ring.
+//   warp 0   : TMA producer (weight panel once per panel job, then A tiles)
+//   warp 1   : tcgen05.mma issuer (one elected lane), accumulators double-buffered in TMEM
+//   warps 2-5: epilogue (tcgen05.ld -> bias / ReLU / residual -> bf16 and/or fp32 stores)
+#include "tc_common.cuh"
+#include "tc_path.cuh"
+
+namespace sfm {
+namespace tc {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int GEMM_THREADS = 192;
+
+struct Barriers {
+  uint64_t w_full, w_empty;
+  uint64_t a_full[STAGES], a_empty[STAGES];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int BN, int KBLOCKS>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
+               const __grid_constant__ CUtensorMap mapW, TcGemm p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [W panel: KBLOCKS * BN * 128][A ring: STAGES * 16 KB][barriers]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + KBLOCKS * BN * 128;
+  Barriers* bars = reinterpret_cast<Barriers*>(sA + STAGES * A_STAGE_BYTES);
+  constexpr int TMEM_COLS = 2 * BN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapA2);
+    tma_prefetch_desc(&mapW);
+    mbar_init(&bars->w_full, 1);
+    mbar_init(&bars->w_empty, 1);
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&bars->a_full[s], 1);
+      mbar_init(&bars->a_empty[s], 1);
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&bars->acc_full[b], 1);
+      mbar_init(&bars->acc_empty[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  // work decomposition: slot -> panel jobs (batch, panel); sub -> m tiles of that job
+  const int n_pj = p.batch * p.num_panels;
+  const int slot = blockIdx.x / p.cpp, sub = blockIdx.x % p.cpp;
+  const int n_slots = gridDim.x / p.cpp;
+  const int k1_blocks = p.K1 / BK;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0, phase = 0, wphase = 0;
+      for (int pj = slot; pj < n_pj; pj += n_slots) {
+        const int b = pj / p.num_panels, panel = pj % p.num_panels;
+        if (pj != slot) {
+          mbar_wait(&bars->w_empty, wphase);
+          wphase ^= 1;
+        }
+        mbar_arrive_expect_tx(&bars->w_full, KBLOCKS * BN * 128);
+        const int wrow = p.w_row_base + b * p.w_row_stride + panel * BN;
+        for (int kb = 0; kb < KBLOCKS; kb++) tma_load_2d(sW + kb * BN * 128, &mapW, &bars->w_full, kb * BK, wrow);
+        for (int mt = sub; mt < p.num_m_tiles; mt += p.cpp) {
+          const int arow = b * p.a_row_stride + mt * BM;
+          for (int kb = 0; kb < KBLOCKS; kb++) {
+            mbar_wait(&bars->a_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&bars->a_full[stage], A_STAGE_BYTES);
+            if (kb < k1_blocks)
+              tma_load_2d(sA + stage * A_STAGE_BYTES, &mapA, &bars->a_full[stage], kb * BK, arow);
+            else
+              tma_load_2d(sA + stage * A_STAGE_BYTES, &mapA2, &bars->a_full[stage], (kb - k1_blocks) * BK, arow);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0);
+      int stage = 0, phase = 0, wphase = 0, tile = 0;
+      for (int pj = slot; pj < n_pj; pj += n_slots) {
+        mbar_wait(&bars->w_full, wphase);
+        wphase ^= 1;
+        tc_fence_after();
+        for (int mt = sub; mt < p.num_m_tiles; mt += p.cpp, tile++) {
+          const int buf = tile & 1;
+          mbar_wait(&bars->acc_empty[buf], ((tile >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          for (int kb = 0; kb < KBLOCKS; kb++) {
+            mbar_wait(&bars->a_full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+            const uint32_t b_addr = smem_u32(sW + kb * BN * 128);
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++) {
+              uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+              uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+              umma_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            }
+            umma_commit(&bars->a_empty[stage]);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit(&bars->acc_full[buf]);
+        }
+        umma_commit(&bars->w_empty);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int quad = warp & 3;
+    int tile = 0;
+    for (int pj = slot; pj < n_pj; pj += n_slots) {
+      const int b = pj / p.num_panels, panel = pj % p.num_panels;
+      for (int mt = sub; mt < p.num_m_tiles; mt += p.cpp, tile++) {
+        const int buf = tile & 1;
+        mbar_wait(&bars->acc_full[buf], (tile >> 1) & 1);
+        tc_fence_after();
+        const int row = mt * BM + quad * 32 + lane;  // row inside this batch
+        const bool row_ok = row < p.M;
+        __nv_bfloat16* oh = p.out_h ? p.out_h + b * p.out_h_bstride + (long long)row * p.out_h_ld : nullptr;
+        float* of = p.out_f ? p.out_f + b * p.out_f_bstride + (long long)row * p.out_f_ld : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; c++) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN + c * 32, r);
+          tmem_wait_ld();
+          const int n0 = panel * BN + c * 32;
+          if (row_ok && n0 < p.N) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              float x = __uint_as_float(r[j]) * p.alpha;
+              if (p.bias != nullptr && n0 + j < p.N) x += __ldg(p.bias + n0 + j);
+              if (p.relu) x = fmaxf(x, 0.f);
+              v[j] = x;
+            }
+            const bool full = n0 + 32 <= p.N;
+            if (of != nullptr) {
+              if (full && p.vec_f) {
+                float4* dst = reinterpret_cast<float4*>(of + n0);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                  float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                  if (p.accumulate_f) {
+                    float4 old = dst[j];
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                    v[4 * j] = o.x; v[4 * j + 1] = o.y; v[4 * j + 2] = o.z; v[4 * j + 3] = o.w;
+                  }
+                  dst[j] = o;
+                }
+              } else {
+                for (int j = 0; j < 32 && n0 + j < p.N; j++) {
+                  float o = v[j];
+                  if (p.accumulate_f) {
+                    o += of[n0 + j];
+                    v[j] = o;
+                  }
+                  of[n0 + j] = o;
+                }
+              }
+            }
+            if (oh != nullptr) {
+              if (full) {
+                uint4* dst = reinterpret_cast<uint4*>(oh + n0);
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                  dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                      pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+              } else {
+                for (int j = 0; j < 32 && n0 + j < p.N; j++) oh[n0 + j] = __float2bfloat16(v[j]);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+template <int BN, int KBLOCKS>
+int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mW, int num_sms,
+           cudaStream_t st) {
+  TcGemm p = p_in;
+  p.num_panels = cdiv(p.N, BN);
+  p.num_m_tiles = cdiv(p.M, BM);
+  const int n_pj = p.batch * p.num_panels;
+  int cpp = num_sms / n_pj;
+  if (cpp < 1) cpp = 1;
+  if (cpp > p.num_m_tiles) cpp = p.num_m_tiles;
+  int n_slots = num_sms / cpp;
+  if (n_slots > n_pj) n_slots = n_pj;
+  p.cpp = cpp;
+  const size_t smem = (size_t)KBLOCKS * BN * 128 + STAGES * A_STAGE_BYTES + sizeof(Barriers) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    SFM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, KBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  tc_gemm_kernel<BN, KBLOCKS><<<n_slots * cpp, GEMM_THREADS, smem, st>>>(mA, mA2, mW, p);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                   uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return SFM_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r, base,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows);
+    return SFM_ERR_CUDA;
+  }
+  return SFM_OK;
+}
+
+int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
+  SFM_REQUIRE(p.K == 256 || p.K == 512, "tc_gemm: K must be 256 or 512 (got %d)", p.K);
+  SFM_REQUIRE(p.M > 0 && p.N > 0 && p.batch > 0, "tc_gemm: bad dims");
+  SFM_REQUIRE(p.K1 % 64 == 0 && p.K1 > 0 && p.K1 <= p.K, "tc_gemm: bad split point");
+  SFM_REQUIRE(p.out_h == nullptr || (p.out_h_ld % 8 == 0 && p.out_h_bstride % 8 == 0),
+              "tc_gemm: bf16 output leading dimension must be a multiple of 8");
+  CUtensorMap mA, mA2, mW;
+  SFM_TRY(make_tmap_bf16(&mA, p.A, p.a_rows, p.K1, p.lda, BM));
+  if (p.K1 < p.K)
+    SFM_TRY(make_tmap_bf16(&mA2, p.A2, p.a_rows, p.K - p.K1, p.lda2, BM));
+  else
+    mA2 = mA;
+  const bool wide = (p.K == 256) && (p.N > 128);
+  SFM_TRY(make_tmap_bf16(&mW, p.W, p.w_rows, p.K, p.ldw, wide ? 256 : 128));
+  TcGemm q = p;
+  q.vec_f = (p.out_f != nullptr) && (p.out_f_ld % 4 == 0) && (p.out_f_bstride % 4 == 0) &&
+            ((reinterpret_cast<uintptr_t>(p.out_f) & 15) == 0);
+  if (p.K == 256) {
+    if (wide) return launch<256, 4>(q, mA, mA2, mW, num_sms, st);
+    return launch<128, 4>(q, mA, mA2, mW, num_sms, st);
+  }
+  return launch<128, 8>(q, mA, mA2, mW, num_sms, st);
+}
+
+}  // namespace tc
+}  // namespace sfm

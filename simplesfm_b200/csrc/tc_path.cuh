@@ -6,12 +6,64 @@ namespace sfm {
 
 struct TcSgBuffers {
   __nv_bfloat16 *xh, *qkv, *msgp, *msg, *hid, *mdh;
-  float *hid32, *stats, *mean, *var, *t0, *t1;
+  float *stat_part, *mean, *var, *t0, *t1;
+  int stat_blocks;
 };
 
 void tc_sg_carve(Arena& a, const SgCall& c, TcSgBuffers& b);
 // X: fp32 master descriptors [T,256] (frontend output), kin [T,4]; writes scores [B,K0,K1] f32
 int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float* scores, const TcSgBuffers& b,
                   cudaStream_t st);
+// keypoint encoder on the fp32 SIMT path (shared by both precisions): X += kenc(kin)
+int kenc_forward_f32(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float* t0, float* t1, float* mean,
+                     float* var, cudaStream_t st);
 
+namespace tc {
+
+// D_b[M,N] = alpha * A_b[M,K] * W_b[N,K]^T + bias   (bf16 operands, fp32 accumulation in TMEM)
+struct TcGemm {
+  const __nv_bfloat16* A = nullptr;   // [a_rows, K1] row-major (lda)
+  const __nv_bfloat16* A2 = nullptr;  // [a_rows, K-K1] (lda2): concat along K (MLP input [x | message])
+  const __nv_bfloat16* W = nullptr;   // [w_rows, K] (ldw)
+  long long a_rows = 0, w_rows = 0;
+  int lda = 0, lda2 = 0, ldw = 0;
+  int M = 0, N = 0, K = 0, K1 = 0;
+  int batch = 1;
+  int a_row_stride = 0;                  // A row offset per batch
+  int w_row_base = 0, w_row_stride = 0;  // W row offset = base + b * stride
+  const float* bias = nullptr;
+  float alpha = 1.f;
+  int relu = 0;
+  __nv_bfloat16* out_h = nullptr;
+  long long out_h_ld = 0, out_h_bstride = 0;
+  float* out_f = nullptr;
+  long long out_f_ld = 0, out_f_bstride = 0;
+  int accumulate_f = 0;  // out_f += result (residual stream); out_h then holds bf16(out_f)
+  // filled by the launcher
+  int vec_f = 0, num_panels = 0, num_m_tiles = 0, cpp = 1;
+};
+int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st);
+
+// fused multi-head attention for both sides of one GNN layer (superglue.py:85-108):
+// message[q] = softmax(Q K^T / 8) V per head; Q/K/V read from the fused projection buffer
+// qkv [T, 768] (q | k | v, heads contiguous), output msgp [T, 256] bf16.
+struct TcAttn {
+  const __nv_bfloat16* qkv = nullptr;
+  long long rows_total = 0;
+  __nv_bfloat16* out = nullptr;
+  int B = 0;
+  int Nq[2] = {0, 0}, Nk[2] = {0, 0};
+  long long q_row0[2] = {0, 0}, k_row0[2] = {0, 0};
+};
+int tc_attention(const TcAttn& p, cudaStream_t st);
+
+// elementwise / reduction helpers of the bf16 path
+int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);
+int stat_blocks_for(long long T0, long long T1);
+int col_stats_bf16(const __nv_bfloat16* X, int C, long long T0, long long T1, float* partial, float* mean, float* var,
+                   cudaStream_t st);
+int bn_relu_bf16(__nv_bfloat16* X, int C, long long T0, long long T1, const float* mean, const float* var,
+                 const float* gamma, const float* beta, float eps, cudaStream_t st);
+
+}  // namespace tc
 }  // namespace sfm

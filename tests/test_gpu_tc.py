@@ -1,0 +1,129 @@
+"""GPU tests of the tcgen05 (bf16) kernels against torch fp32 math on the same bf16-rounded inputs,
+and of the bf16 SuperGlue path against the fp32 path / reference goldens (match-set agreement
+>= 99.5 %, the bar BASELINE.json states for the bf16 precision mode)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, t
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def handle(dev):
+    from simplesfm_b200 import _lib
+    return _lib.Handle(dev)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("M,N,K,K1", [(128, 256, 256, 256), (1000, 768, 256, 256), (4096, 512, 512, 256),
+                                      (777, 256, 512, 512), (20480, 768, 256, 256), (300, 65, 256, 256)])
+def test_tc_gemm(handle, dev, M, N, K, K1):
+    from simplesfm_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    A = torch.randn(M, K, generator=g).to(dev).bfloat16()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(dev)
+    A1 = A[:, :K1].contiguous()
+    A2 = A[:, K1:].contiguous() if K1 < K else None
+    out_h = torch.zeros(M, N, dtype=torch.bfloat16, device=dev)
+    out_f = torch.zeros(M, N, dtype=torch.float32, device=dev)
+    _lib.check(_lib.lib().sfm_tc_gemm(handle.h, A1.data_ptr(), None if A2 is None else A2.data_ptr(), W.data_ptr(),
+                                      M, N, K, K1, bias.data_ptr(), 0.5, 1, out_h.data_ptr() if N % 8 == 0 else None,
+                                      out_f.data_ptr(), 0, _stream()))
+    ref = torch.relu(0.5 * (A.float() @ W.float().t()) + bias)
+    torch.testing.assert_close(out_f, ref, rtol=2e-3, atol=2e-3)
+    if N % 8 == 0:
+        torch.testing.assert_close(out_h.float(), ref, rtol=2e-2, atol=2e-2)
+    # residual accumulate: out_f += result ; out_h = bf16(out_f)
+    base = torch.randn(M, N, generator=g).to(dev)
+    out_f2 = base.clone()
+    _lib.check(_lib.lib().sfm_tc_gemm(handle.h, A1.data_ptr(), None if A2 is None else A2.data_ptr(), W.data_ptr(),
+                                      M, N, K, K1, bias.data_ptr(), 1.0, 0, out_h.data_ptr() if N % 8 == 0 else None,
+                                      out_f2.data_ptr(), 1, _stream()))
+    ref2 = base + A.float() @ W.float().t() + bias
+    torch.testing.assert_close(out_f2, ref2, rtol=2e-3, atol=2e-3)
+    if N % 8 == 0:
+        torch.testing.assert_close(out_h.float(), ref2, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("B,N0,N1,cross", [(1, 256, 256, False), (2, 512, 384, True), (3, 333, 251, True),
+                                           (3, 333, 251, False), (1, 2048, 2048, True), (2, 100, 60, True)])
+def test_tc_attention(handle, dev, B, N0, N1, cross):
+    from simplesfm_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + N0)
+    T0, T1 = B * N0, B * N1
+    T = T0 + T1
+    qkv = (torch.randn(T, 768, generator=g) * 1.5).to(dev).bfloat16()
+    out = torch.zeros(T, 256, dtype=torch.bfloat16, device=dev)
+    Nk0, Nk1 = (N1, N0) if cross else (N0, N1)
+    k0, k1 = (T0, 0) if cross else (0, T0)
+    _lib.check(_lib.lib().sfm_tc_attention(handle.h, qkv.data_ptr(), T, B, N0, Nk0, 0, k0, N1, Nk1, T0, k1,
+                                           out.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    f = qkv.float()
+    for side, (Nq, Nk, q0, kk0) in enumerate(((N0, Nk0, 0, k0), (N1, Nk1, T0, k1))):
+        for b in range(B):
+            q = f[q0 + b * Nq:q0 + (b + 1) * Nq, 0:256].view(Nq, 4, 64).permute(1, 0, 2)
+            k = f[kk0 + b * Nk:kk0 + (b + 1) * Nk, 256:512].view(Nk, 4, 64).permute(1, 0, 2)
+            v = f[kk0 + b * Nk:kk0 + (b + 1) * Nk, 512:768].view(Nk, 4, 64).permute(1, 0, 2)
+            p = torch.softmax(q @ k.transpose(1, 2) / 8.0, dim=-1)
+            ref = (p @ v).permute(1, 0, 2).reshape(Nq, 256)
+            got = out[q0 + b * Nq:q0 + (b + 1) * Nq].float()
+            torch.testing.assert_close(got, ref, rtol=3e-2, atol=3e-2)
+
+
+def _agreement(a, b):
+    a, b = a.cpu().numpy(), b.cpu().numpy()
+    both = (a > -1) | (b > -1)
+    return float(((a == b) & both).sum()) / max(int(both.sum()), 1)
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_superglue_bf16_match_agreement(sg_weights, dev, mode):
+    """bf16 (stated precision) vs the fp32 path on the same inputs: >= 99.5 % match-set agreement."""
+    from simplesfm_b200 import synthetic
+    from simplesfm_b200.models.superglue import SuperGlue
+    B, K = 4, 1024
+    fr = synthetic.feature_scene(2 * B, K, seed=9)
+    data = {"descriptors0": torch.stack([fr[i][0] for i in range(B)]).to(dev),
+            "descriptors1": torch.stack([fr[B + i][0] for i in range(B)]).to(dev),
+            "keypoints0": torch.stack([fr[i][1] for i in range(B)]).to(dev),
+            "keypoints1": torch.stack([fr[B + i][1] for i in range(B)]).to(dev),
+            "scores0": torch.stack([fr[i][2] for i in range(B)]).to(dev),
+            "scores1": torch.stack([fr[B + i][2] for i in range(B)]).to(dev),
+            "image0": torch.zeros(B, 1, 480, 640), "image1": torch.zeros(B, 1, 480, 640)}
+    ref = SuperGlue(sg_weights, sinkhorn_iterations=20, match_threshold=0.2, bn_mode=mode, precision="fp32",
+                    device=dev)(data)
+    out = SuperGlue(sg_weights, sinkhorn_iterations=20, match_threshold=0.2, bn_mode=mode, precision="bf16",
+                    device=dev)(data)
+    agree = _agreement(out["matches0"], ref["matches0"])
+    n_ref = int((ref["matches0"] > -1).sum())
+    print(f"bf16 vs fp32 [{mode}]: agreement {agree:.4f} over {n_ref} reference matches")
+    assert n_ref > 200
+    assert agree >= 0.995
+
+
+def test_superglue_bf16_golden_ragged(sg_weights, dev):
+    """Ragged keypoint counts (96 / 80) through the bf16 path against the reference golden matches."""
+    from simplesfm_b200.models.superglue import SuperGlue
+    g = load_golden("sg_b2_train_it20")
+    data = {k: t(g[k]).to(dev) for k in ("descriptors0", "descriptors1", "keypoints0", "keypoints1", "scores0",
+                                          "scores1")}
+    data["image0"] = data["image1"] = torch.zeros(2, 1, 480, 640)
+    out = SuperGlue(sg_weights, sinkhorn_iterations=20, match_threshold=0.2, precision="bf16", device=dev)(data)
+    a, b = out["matches0"].cpu().numpy(), g["matches0"]
+    both = (a > -1) | (b > -1)
+    agree = ((a == b) & both).sum() / max(both.sum(), 1)
+    print(f"bf16 vs reference golden: agreement {agree:.4f} over {int((b > -1).sum())} matches")
+    assert agree >= 0.97            # tiny case: one flipped match is > 1 %
