@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--iters", type=int, default=20, help="sinkhorn_iterations (Matcher default 20)")
     ap.add_argument("--bn", default="train", choices=["train", "eval"])
     ap.add_argument("--cpu-pairs", type=int, default=2, help="pairs in the bounded CPU sample")
+    ap.add_argument("--fuse-chunks", type=int, default=8, help="Matcher chunks launched together (BN stats stay per chunk)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -163,7 +164,7 @@ def run_ours(a):
     spw, sgw = synthetic.superpoint_state_dict(0), synthetic.superglue_state_dict(0, "indoor")
     m = Matcher(spw, 4, 0.005, matcher_type="super_glue", super_glue_weights_path=sgw, match_threshold=0.4,
                 sinkhorn_iterations=a.iters, super_glue_batch=a.batch, bn_mode=a.bn, precision=a.precision,
-                device=dev, shard_pairs=False)
+                device=dev, shard_pairs=False, fuse_chunks=a.fuse_chunks)
     scene = synthetic.feature_scene(a.images, a.kp, seed=rank)
     host = [(d.pin_memory(), k.pin_memory(), s.pin_memory()) for d, k, s in scene]
     img = torch.zeros(1, 480, 640, device=dev)
@@ -247,7 +248,7 @@ def run_ours(a):
             "vs_baseline": None, "dtype": "bf16" if a.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "pairs_per_step_per_gpu": n_pairs,
                        "sinkhorn_iterations": a.iters, "bn_mode": a.bn, "super_glue_batch": a.batch,
-                       "precision": a.precision, "match_threshold": 0.4,
+                       "precision": a.precision, "match_threshold": 0.4, "fused_chunks_per_launch": a.fuse_chunks,
                        "l2": "working set exceeds L2 (feature records 105 MB + per-chunk activations)"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -114,8 +114,11 @@ SFM_API int sfm_sample_descriptors(const float* dmap_nhwc, int n_img, int h, int
  * A batch of B pairs is (idx0[b], idx1[b]) into those records (NULL = identity, i.e. the record
  * arrays ARE the (B,256,K) batch tensors of the reference).  K0/K1: keypoints used per side (the
  * caller applies the reference's chunk-minimum truncation, matcher.py:82-91).
+ * chunk_groups (>= 1): the B pairs are `chunk_groups` consecutive Matcher chunks of B/chunk_groups
+ * pairs fused into one launch; train-mode BatchNorm statistics stay per chunk and side, so the
+ * results equal `chunk_groups` separate calls (matcher.py:73-101 semantics) at better GPU occupancy.
  * Outputs: matches0 (B,K0) i64, matches1 (B,K1) i64, matching_scores0/1 f32. */
-SFM_API size_t sfm_superglue_workspace_bytes(int B, int K0, int K1, int precision);
+SFM_API size_t sfm_superglue_workspace_bytes(int B, int K0, int K1, int precision, int chunk_groups);
 SFM_API int sfm_superglue_forward(sfm_handle_t h,
                           const float* desc0, const float* kpts0, const float* scores0, int ldk0, int kcap0,
                           const int* idx0,
@@ -123,12 +126,13 @@ SFM_API int sfm_superglue_forward(sfm_handle_t h,
                           const int* idx1,
                           int B, int K0, int K1, int H0, int W0, int H1, int W1,
                           int sinkhorn_iterations, float match_threshold, int bn_mode, int precision,
+                          int chunk_groups,
                           int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
                           void* workspace, size_t workspace_bytes, void* stream);
 /* parity taps into the forward workspace: which = 0 descriptors after kenc (token-major
  * [B*K0 + B*K1, 256]), 1 after the GNN, 2 score matrix [B,K0,K1], 3 u [B,K0+1], 4 v [B,K1+1] */
-SFM_API int sfm_superglue_tap(int B, int K0, int K1, int precision, int which, void* workspace, size_t workspace_bytes,
-                      float** out_ptr, size_t* out_floats);
+SFM_API int sfm_superglue_tap(int B, int K0, int K1, int precision, int chunk_groups, int which, void* workspace,
+                      size_t workspace_bytes, float** out_ptr, size_t* out_floats);
 
 /* log_optimal_transport (superglue.py:151-171): scores (B,N,M) -> Z (B,N+1,M+1) */
 SFM_API size_t sfm_sinkhorn_workspace_bytes(int B, int N, int M);

@@ -45,15 +45,15 @@ _SIGNATURES = {
     "sfm_simple_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sfm_sample_descriptors": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_int, C.c_void_p, C.c_void_p]),
-    "sfm_superglue_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "sfm_superglue_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
     "sfm_superglue_forward": (C.c_int, [C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                        C.c_int, C.c_float, C.c_int, C.c_int,
+                                        C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_size_t, C.c_void_p]),
-    "sfm_superglue_tap": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+    "sfm_superglue_tap": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "sfm_sinkhorn_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "sfm_log_optimal_transport": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p,

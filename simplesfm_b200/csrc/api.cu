@@ -283,6 +283,25 @@ int sfm_load_superglue(sfm_handle_t h, const float* packed, size_t n) {
     SFM_TRY(upload_bf16(h, W1, &L.W1_h));
     SFM_TRY(upload_bf16(h, W1f, &L.W1f_h));
     SFM_TRY(upload_bf16(h, W2, &L.W2_h));
+    // fold the attention merge conv into the first MLP conv (exact algebra, done in double)
+    for (int variant = 0; variant < 2; variant++) {
+      const std::vector<float>& Wa = variant ? W1f : W1;
+      const std::vector<float>& ba = variant ? b1f : b1;
+      std::vector<float> Wc((size_t)512 * 512), bc(512);
+      for (int o = 0; o < 512; o++) {
+        for (int c = 0; c < 256; c++) Wc[(size_t)o * 512 + c] = Wa[(size_t)o * 512 + c];
+        double bacc = ba[o];
+        for (int k = 0; k < 256; k++) bacc += (double)Wa[(size_t)o * 512 + 256 + k] * bm[k];
+        bc[o] = (float)bacc;
+        for (int c = 0; c < 256; c++) {
+          double acc = 0.0;
+          for (int k = 0; k < 256; k++) acc += (double)Wa[(size_t)o * 512 + 256 + k] * Wmp[(size_t)k * 256 + c];
+          Wc[(size_t)o * 512 + 256 + c] = (float)acc;
+        }
+      }
+      SFM_TRY(upload_bf16(h, Wc, variant ? &L.W1cf_h : &L.W1c_h));
+      SFM_TRY(upload(h, bc, variant ? &L.b1cf : &L.b1c));
+    }
   }
   std::vector<float> Wf = r.take(256 * 256), bf = r.take(256);
   SFM_TRY(upload(h, Wf, &w.Wf));
@@ -337,16 +356,16 @@ int sfm_sample_descriptors(const float* dmap_nhwc, int n_img, int h, int w, cons
 }
 
 // ---- SuperGlue --------------------------------------------------------------------------------
-static SgCall shape_call(int B, int K0, int K1, int precision) {
+static SgCall shape_call(int B, int K0, int K1, int precision, int groups) {
   SgCall c;
   memset(&c, 0, sizeof(c));
-  c.B = B; c.K0 = K0; c.K1 = K1; c.precision = precision;
+  c.B = B; c.K0 = K0; c.K1 = K1; c.precision = precision; c.groups = groups;
   return c;
 }
 
-size_t sfm_superglue_workspace_bytes(int B, int K0, int K1, int precision) {
+size_t sfm_superglue_workspace_bytes(int B, int K0, int K1, int precision, int chunk_groups) {
   size_t need = 0;
-  SgCall c = shape_call(B, K0, K1, precision);
+  SgCall c = shape_call(B, K0, K1, precision, chunk_groups);
   if (sg_forward(nullptr, c, nullptr, 0, true, &need, 0, nullptr, nullptr, 0) != SFM_OK) return 0;
   return need;
 }
@@ -355,8 +374,8 @@ int sfm_superglue_forward(sfm_handle_t h, const float* desc0, const float* kpts0
                           int kcap0, const int* idx0, const float* desc1, const float* kpts1, const float* scores1,
                           int ldk1, int kcap1, const int* idx1, int B, int K0, int K1, int H0, int W0, int H1, int W1,
                           int sinkhorn_iterations, float match_threshold, int bn_mode, int precision,
-                          int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1, void* ws,
-                          size_t ws_bytes, void* stream) {
+                          int chunk_groups, int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
+                          void* ws, size_t ws_bytes, void* stream) {
   SFM_REQUIRE(h, "sfm_superglue_forward: NULL handle");
   SFM_REQUIRE(B == 0 || (desc0 && kpts0 && scores0 && desc1 && kpts1 && scores1), "sfm_superglue_forward: NULL input");
   SFM_REQUIRE(B == 0 || (matches0 && matches1 && mscores0 && mscores1), "sfm_superglue_forward: NULL output");
@@ -367,14 +386,15 @@ int sfm_superglue_forward(sfm_handle_t h, const float* desc0, const float* kpts0
   c.desc1 = desc1; c.kpts1 = kpts1; c.scores1 = scores1; c.ldk1 = ldk1; c.kcap1 = kcap1; c.idx1 = idx1;
   c.B = B; c.K0 = K0; c.K1 = K1; c.H0 = H0; c.W0 = W0; c.H1 = H1; c.W1 = W1;
   c.iters = sinkhorn_iterations; c.thr = match_threshold; c.bn_mode = bn_mode; c.precision = precision;
+  c.groups = chunk_groups;
   c.m0 = (long long*)matches0; c.m1 = (long long*)matches1; c.ms0 = mscores0; c.ms1 = mscores1;
   return sg_forward(h, c, ws, ws_bytes, false, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
 }
 
-int sfm_superglue_tap(int B, int K0, int K1, int precision, int which, void* ws, size_t ws_bytes, float** out_ptr,
-                      size_t* out_floats) {
+int sfm_superglue_tap(int B, int K0, int K1, int precision, int chunk_groups, int which, void* ws, size_t ws_bytes,
+                      float** out_ptr, size_t* out_floats) {
   SFM_REQUIRE(out_ptr && out_floats, "sfm_superglue_tap: NULL output");
-  SgCall c = shape_call(B, K0, K1, precision);
+  SgCall c = shape_call(B, K0, K1, precision, chunk_groups);
   return sg_forward(nullptr, c, ws, ws_bytes, false, nullptr, which, out_ptr, out_floats, 0);
 }
 

@@ -1,0 +1,25 @@
+// Train-mode BatchNorm1d statistics + fused normalise/ReLU (reference superglue.py:56-57 as run:
+// batch statistics over all (B x N) columns of one side, biased variance, eps 1e-5).
+// Two token groups (side 0 rows [0,T0), side 1 rows [T0,T0+T1)) get separate statistics, exactly
+// like the reference's two separate module calls (superglue.py:254-255, 137).
+#pragma once
+#include "common.cuh"
+
+namespace sfm {
+
+// Rows [0,T0) belong to side 0 and [T0,T0+T1) to side 1; each side is cut into G equal statistic
+// groups (G > 1 when several Matcher chunks are fused into one launch: every chunk keeps its own
+// batch statistics, exactly as if it had been run alone).
+struct BnGroups {
+  long long T0, T1;
+  int G;
+};
+int bn_stat_blocks(const BnGroups& g);
+// partial: [bn_stat_blocks, C, 2] floats; scale/shift: [2 * G, C]  (y = relu(x * scale + shift))
+template <typename T>
+int bn_train_stats(const T* X, int ld, int C, const BnGroups& g, const float* gamma, const float* beta, float eps,
+                   float* partial, float* scale, float* shift, cudaStream_t st);
+template <typename T>
+int bn_apply_relu(T* X, int ld, int C, const BnGroups& g, const float* scale, const float* shift, cudaStream_t st);
+
+}  // namespace sfm

@@ -29,6 +29,9 @@ struct SgLayer {
   float* b2;
   // bf16 copies for the tcgen05 path
   __nv_bfloat16 *Wqkv_h, *Wm_h, *W1_h, *W1f_h, *W2_h;
+  // merge conv folded into the MLP input layer: mlp0([x | merge(a)]) = [W1x | W1m Wm] [x | a] + (b1 + W1m bm)
+  __nv_bfloat16 *W1c_h, *W1cf_h;   // [512, 512] train / eval-folded
+  float *b1c, *b1cf;
 };
 
 struct SgWeights {
@@ -95,6 +98,7 @@ struct SgCall {
   int iters;
   float thr;
   int bn_mode, precision;
+  int groups;  // number of BatchNorm statistic groups (fused Matcher chunks); B % groups == 0
   long long *m0, *m1;
   float *ms0, *ms1;
 };

@@ -3,14 +3,16 @@
 #include "context.cuh"
 #include "gemm_f32.cuh"
 #include "sg_kernels.cuh"
+#include "bn_kernels.cuh"
 #include "tc_path.cuh"
+#include <stdlib.h>
 
 namespace sfm {
 
 namespace {
 
 struct SgBuffers {
-  float *X, *xk, *kin, *t0, *t1, *qkv, *msgp, *msg, *hid, *att, *mean, *var, *md, *scores, *u, *v, *part, *max0, *max1;
+  float *X, *xk, *kin, *t0, *t1, *qkv, *msgp, *msg, *hid, *att, *bn_part, *bn_scale, *bn_shift, *md, *scores, *u, *v, *part, *max0, *max1;
   int *counters, *idx0, *idx1;
   int R, ldS;
 };
@@ -22,16 +24,18 @@ int carve(Arena& a, const SgCall& c, SgBuffers& b) {
   b.X = a.get<float>(T * 256);
   b.xk = a.get<float>(T * 256);
   b.kin = a.get<float>(T * 4);
+  b.t0 = a.get<float>(T * 256);   // keypoint-encoder ping-pong (fp32 SIMT on both precision paths)
+  b.t1 = a.get<float>(T * 256);
+  const int G = c.groups > 0 ? c.groups : 1;
+  b.bn_part = a.get<float>((size_t)bn_stat_blocks(BnGroups{T0, T1, G}) * 512 * 2);
+  b.bn_scale = a.get<float>((size_t)2 * G * 512);
+  b.bn_shift = a.get<float>((size_t)2 * G * 512);
   if (c.precision == 0) {   // fp32-path activations
-    b.t0 = a.get<float>(T * 256);
-    b.t1 = a.get<float>(T * 256);
     b.qkv = a.get<float>(T * 768);
     b.msgp = a.get<float>(T * 256);
     b.msg = a.get<float>(T * 256);
     b.hid = a.get<float>(T * 512);
     b.att = a.get<float>((size_t)c.B * 4 * Kmax * b.ldS);
-    b.mean = a.get<float>(2 * 512);
-    b.var = a.get<float>(2 * 512);
     b.md = a.get<float>(T * 256);
   }
   b.scores = a.get<float>((size_t)c.B * c.K0 * c.K1);
@@ -84,8 +88,8 @@ int attention_f32_raw(const SgBuffers& b, int B, long long q_row0, int Nq, long 
 }
 
 // keypoint encoder (superglue.py:72-82, 254-255): X += kenc(kin); fp32 SIMT on both precision paths
-int kenc_forward_f32(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float* t0, float* t1, float* mean,
-                     float* var, cudaStream_t st) {
+int kenc_forward_f32(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float* t0, float* t1, float* part,
+                     float* scale, float* shift, cudaStream_t st) {
   const SgWeights& w = h->sg;
   const long long T0 = (long long)c.B * c.K0, T1 = (long long)c.B * c.K1, T = T0 + T1;
   const bool train = c.bn_mode == 0;
@@ -100,8 +104,9 @@ int kenc_forward_f32(sfm_ctx* h, const SgCall& c, float* X, const float* kin, fl
     } else if (train) {
       float* out = pp[i & 1];
       SFM_TRY(linear_f32_raw(cur, ld, nullptr, 0, 0, w.kW[i], cin, cout, w.kb[i], out, cout, T, 0, st));
-      SFM_TRY(col_stats_f32(out, cout, cout, (int)T0, (int)T1, mean, var, st));
-      SFM_TRY(bn_relu_f32(out, cout, cout, (int)T0, (int)T1, mean, var, w.kbn[i].gamma, w.kbn[i].beta, 1e-5f, st));
+      const BnGroups gr{T0, T1, c.groups > 0 ? c.groups : 1};
+      SFM_TRY(bn_train_stats<float>(out, cout, cout, gr, w.kbn[i].gamma, w.kbn[i].beta, 1e-5f, part, scale, shift, st));
+      SFM_TRY(bn_apply_relu<float>(out, cout, cout, gr, scale, shift, st));
       cur = out;
       ld = cout;
     } else {
@@ -130,7 +135,7 @@ int forward_f32(sfm_ctx* h, const SgCall& c, const SgBuffers& b, cudaStream_t st
   const bool train = c.bn_mode == 0;
   {
     ProfScope ps(h, SFM_PROF_OTHER, st);
-    SFM_TRY(kenc_forward_f32(h, c, b.X, b.kin, b.t0, b.t1, b.mean, b.var, st));
+    SFM_TRY(kenc_forward_f32(h, c, b.X, b.kin, b.t0, b.t1, b.bn_part, b.bn_scale, b.bn_shift, st));
   }
   SFM_CUDA(cudaMemcpyAsync(b.xk, b.X, T * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));  // parity tap
   // ---- attentional GNN (superglue.py:123-139)
@@ -143,8 +148,11 @@ int forward_f32(sfm_ctx* h, const SgCall& c, const SgBuffers& b, cudaStream_t st
     SFM_TRY(linear_f32(b.msgp, 256, nullptr, 0, 0, L.Wm, 256, 256, L.bm, b.msg, 256, T, 0, st));
     if (train) {
       SFM_TRY(linear_f32(b.X, 256, b.msg, 256, 256, L.W1, 512, 512, L.b1, b.hid, 512, T, 0, st));
-      SFM_TRY(col_stats_f32(b.hid, 512, 512, (int)T0, (int)T1, b.mean, b.var, st));
-      SFM_TRY(bn_relu_f32(b.hid, 512, 512, (int)T0, (int)T1, b.mean, b.var, L.bn1.gamma, L.bn1.beta, 1e-5f, st));
+      ProfScope ps(h, SFM_PROF_OTHER, st);
+      const BnGroups gr{T0, T1, c.groups > 0 ? c.groups : 1};
+      SFM_TRY(bn_train_stats<float>(b.hid, 512, 512, gr, L.bn1.gamma, L.bn1.beta, 1e-5f, b.bn_part, b.bn_scale,
+                                    b.bn_shift, st));
+      SFM_TRY(bn_apply_relu<float>(b.hid, 512, 512, gr, b.bn_scale, b.bn_shift, st));
     } else {
       SFM_TRY(linear_f32(b.X, 256, b.msg, 256, 256, L.W1f, 512, 512, L.b1f, b.hid, 512, T, GEMM_RELU, st));
     }
@@ -170,6 +178,7 @@ int sg_forward(sfm_ctx* h, const SgCall& c, void* ws, size_t ws_bytes, bool dry,
               c.K0, c.K1);
   SFM_REQUIRE(c.precision == 0 || c.precision == 1, "superglue: unknown precision %d", c.precision);
   SFM_REQUIRE(c.bn_mode == 0 || c.bn_mode == 1, "superglue: unknown bn_mode %d", c.bn_mode);
+  SFM_REQUIRE(c.groups >= 0 && (c.groups <= 1 || c.B % c.groups == 0), "superglue: B=%d is not divisible into %d chunk groups", c.B, c.groups);
   Arena a(dry ? nullptr : ws, dry ? 0 : ws_bytes);
   SgBuffers b;
   carve(a, c, b);
@@ -212,11 +221,13 @@ int sg_forward(sfm_ctx* h, const SgCall& c, void* ws, size_t ws_bytes, bool dry,
   if (c.precision == 0) {
     SFM_TRY(forward_f32(h, c, b, st));
   } else {
+    tb.t0 = b.t0; tb.t1 = b.t1; tb.bn_part = b.bn_part; tb.bn_scale = b.bn_scale; tb.bn_shift = b.bn_shift;
     SFM_TRY(tc_sg_forward(h, c, b.X, b.kin, b.scores, tb, st));
   }
   SinkhornArgs s;
   s.S = b.scores; s.B = c.B; s.N = c.K0; s.M = c.K1; s.alpha = h->sg.bin_score; s.iters = c.iters;
   s.u = b.u; s.v = b.v; s.part = b.part; s.counters = b.counters; s.R = b.R;
+  s.fast = c.precision == 1;
   ProfScope ps(h, SFM_PROF_SINKHORN, st);
   SFM_TRY(sinkhorn_run(s, st));
   return sinkhorn_match(s, c.thr, b.max0, b.idx0, b.max1, b.idx1, c.m0, c.m1, c.ms0, c.ms1, st);

@@ -1,4 +1,5 @@
 #include "sg_kernels.cuh"
+#include <stdlib.h>
 
 namespace sfm {
 
@@ -49,75 +50,6 @@ __global__ void __launch_bounds__(256) frontend_kernel(const float* __restrict__
   }
 }
 
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ X, int ld, int C, int g0_rows,
-                                                        int g1_rows, float* __restrict__ mean,
-                                                        float* __restrict__ var) {
-  __shared__ float red[8][33];
-  __shared__ float smean[32];
-  const int g = blockIdx.y;
-  const int r0 = g == 0 ? 0 : g0_rows;
-  const int n = g == 0 ? g0_rows : g1_rows;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  const bool ok = c < C;
-  const float* base = X + (long long)r0 * ld + c;
-  float s = 0.f;
-  if (ok)
-    for (int r = ty; r < n; r += 8) s += base[(long long)r * ld];
-  red[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0) {
-    float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; k++) t += red[k][tx];
-    smean[tx] = n > 0 ? t / (float)n : 0.f;
-  }
-  __syncthreads();
-  const float mu = smean[tx];
-  s = 0.f;
-  if (ok)
-    for (int r = ty; r < n; r += 8) {
-      float dlt = base[(long long)r * ld] - mu;
-      s = fmaf(dlt, dlt, s);
-    }
-  __syncthreads();
-  red[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0 && ok) {
-    float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; k++) t += red[k][tx];
-    mean[g * C + c] = mu;
-    var[g * C + c] = n > 0 ? t / (float)n : 0.f;
-  }
-}
-
-__global__ void bn_relu_kernel(float* __restrict__ X, int ld, int C4, int g0_rows, long long total4,
-                               const float* __restrict__ mean, const float* __restrict__ var,
-                               const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
-  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total4) return;
-  int c4 = gid % C4;
-  long long row = gid / C4;
-  int g = row >= g0_rows ? 1 : 0;
-  int C = C4 * 4;
-  float4 x = *reinterpret_cast<float4*>(X + row * ld + c4 * 4);
-  float4 mu = *reinterpret_cast<const float4*>(mean + g * C + c4 * 4);
-  float4 vr = *reinterpret_cast<const float4*>(var + g * C + c4 * 4);
-  float4 ga = *reinterpret_cast<const float4*>(gamma + c4 * 4);
-  float4 be = *reinterpret_cast<const float4*>(beta + c4 * 4);
-  auto f = [eps](float xv, float m, float v, float gm, float bt) {
-    float a = gm * (1.0f / sqrtf(v + eps));
-    return fmaxf(fmaf(xv - m, a, bt), 0.f);
-  };
-  x.x = f(x.x, mu.x, vr.x, ga.x, be.x);
-  x.y = f(x.y, mu.y, vr.y, ga.y, be.y);
-  x.z = f(x.z, mu.z, vr.z, ga.z, be.z);
-  x.w = f(x.w, mu.w, vr.w, ga.w, be.w);
-  *reinterpret_cast<float4*>(X + row * ld + c4 * 4) = x;
-}
-
 __global__ void softmax_rows_kernel(float* __restrict__ S, long long rows, int M, int ld) {
   long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -139,14 +71,21 @@ __global__ void softmax_rows_kernel(float* __restrict__ S, long long rows, int M
 
 // ------------------------------------------------------------------------------------------
 // Sinkhorn.  Z = [[S, a], [a, a]] is never built: the dustbin row/column are the constant a.
+// FAST = true: ex2.approx based (bf16 precision mode); false: IEEE-accurate expf (fp32 parity mode)
+template <bool FAST>
+__device__ __forceinline__ float ex(float x) {
+  return FAST ? __expf(x) : expf(x);
+}
+template <bool FAST = false>
 __device__ __forceinline__ void lse_push(float& m, float& s, float x) {
   if (x > m) {
-    s = s * expf(m - x) + 1.f;
+    s = s * ex<FAST>(m - x) + 1.f;
     m = x;
   } else {
-    s += expf(x - m);
+    s += ex<FAST>(x - m);
   }
 }
+template <bool FAST = false>
 __device__ __forceinline__ void lse_join(float& m, float& s, float m2, float s2) {
   float mm = fmaxf(m, m2);
   if (mm == -INFINITY) {
@@ -154,11 +93,23 @@ __device__ __forceinline__ void lse_join(float& m, float& s, float m2, float s2)
     m = mm;
     return;
   }
-  s = s * expf(m - mm) + s2 * expf(m2 - mm);
+  s = s * ex<FAST>(m - mm) + s2 * ex<FAST>(m2 - mm);
   m = mm;
+}
+// fold four values into a running (max, sum) with one rescale
+template <bool FAST>
+__device__ __forceinline__ void lse_push4(float& m, float& s, float x0, float x1, float x2, float x3) {
+  const float cm = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+  if (cm == -INFINITY) return;
+  if (cm > m) {
+    s *= ex<FAST>(m - cm);
+    m = cm;
+  }
+  s += (ex<FAST>(x0 - m) + ex<FAST>(x1 - m)) + (ex<FAST>(x2 - m) + ex<FAST>(x3 - m));
 }
 
 // u_i = log_mu_i - LSE_j(Z_ij + v_j); one warp per row (rows 0..N, row N is the dustbin row)
+template <bool FAST>
 __global__ void __launch_bounds__(256) sk_row_kernel(const float* __restrict__ S, int N, int M, float alpha,
                                                      const float* __restrict__ v, float* __restrict__ u, float norm,
                                                      float log_mu_bin) {
@@ -171,25 +122,24 @@ __global__ void __launch_bounds__(256) sk_row_kernel(const float* __restrict__ S
   if (row < N) {
     const float* sr = S + ((long long)b * N + row) * M;
     int j = lane;
-    for (; j + 96 < M; j += 128) {
-      float x0 = sr[j] + vb[j], x1 = sr[j + 32] + vb[j + 32], x2 = sr[j + 64] + vb[j + 64],
-            x3 = sr[j + 96] + vb[j + 96];
-      float cm = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
-      if (cm > m) {
-        s *= expf(m - cm);
-        m = cm;
-      }
-      s += expf(x0 - m) + expf(x1 - m) + expf(x2 - m) + expf(x3 - m);
+    for (; j + 224 < M; j += 256) {   // 8 independent loads in flight per lane
+      float x[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) x[q] = sr[j + 32 * q] + vb[j + 32 * q];
+      lse_push4<FAST>(m, s, x[0], x[1], x[2], x[3]);
+      lse_push4<FAST>(m, s, x[4], x[5], x[6], x[7]);
     }
-    for (; j < M; j += 32) lse_push(m, s, sr[j] + vb[j]);
+    for (; j + 96 < M; j += 128)
+      lse_push4<FAST>(m, s, sr[j] + vb[j], sr[j + 32] + vb[j + 32], sr[j + 64] + vb[j + 64], sr[j + 96] + vb[j + 96]);
+    for (; j < M; j += 32) lse_push<FAST>(m, s, sr[j] + vb[j]);
   } else {
-    for (int j = lane; j < M; j += 32) lse_push(m, s, alpha + vb[j]);
+    for (int j = lane; j < M; j += 32) lse_push<FAST>(m, s, alpha + vb[j]);
   }
-  if (lane == 0) lse_push(m, s, alpha + vb[M]);
+  if (lane == 0) lse_push<FAST>(m, s, alpha + vb[M]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
-    lse_join(m, s, m2, s2);
+    lse_join<FAST>(m, s, m2, s2);
   }
   if (lane == 0) u[(long long)b * (N + 1) + row] = (row < N ? norm : log_mu_bin) - (m + logf(s));
 }
@@ -197,7 +147,7 @@ __global__ void __launch_bounds__(256) sk_row_kernel(const float* __restrict__ S
 // column pass.  MODE 0: v_j = log_nu_j - LSE_i(Z_ij + u_i).  MODE 1: column argmax of
 // ((S_ij + u_i) + v_j) - norm over i < N (first index on ties).
 // grid (colblocks(128), R, B), 256 threads: warp w takes rows r0 + w, r0 + w + 8, ...
-template <int MODE>
+template <int MODE, bool FAST>
 __global__ void __launch_bounds__(256) sk_col_kernel(const float* __restrict__ S, int N, int M, float alpha,
                                                      const float* __restrict__ u, const float* __restrict__ vin,
                                                      float* __restrict__ out_v, float* __restrict__ part,
@@ -224,16 +174,29 @@ __global__ void __launch_bounds__(256) sk_col_kernel(const float* __restrict__ S
     int j = c0 + lane + 32 * q;
     vj[q] = (MODE == 1 && j < M) ? vin[(long long)b * (M + 1) + j] : 0.f;
   }
-  for (int i = r0 + warp; i < r1; i += 8) {
-    const float ui = ub[i];
-    const float* sr = Sb + (long long)i * M + c0 + lane;
+  if (MODE == 0) {
+    // each warp folds 4 consecutive rows per step: 16 independent loads in flight per lane
+    for (int i = r0 + warp * 4; i < r1; i += 32) {
+      float x[4][4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      int j = c0 + lane + 32 * q;
-      if (j < M) {
-        if (MODE == 0) {
-          lse_push(m[q], s[q], sr[32 * q] + ui);
-        } else {
+      for (int rr = 0; rr < 4; rr++) {
+        const bool rok = i + rr < r1;
+        const float ui = rok ? ub[i + rr] : 0.f;
+        const float* sr = Sb + (long long)(i + rr) * M + c0 + lane;
+#pragma unroll
+        for (int q = 0; q < 4; q++) x[rr][q] = (rok && c0 + lane + 32 * q < M) ? sr[32 * q] + ui : -INFINITY;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) lse_push4<FAST>(m[q], s[q], x[0][q], x[1][q], x[2][q], x[3][q]);
+    }
+  } else {
+    for (int i = r0 + warp; i < r1; i += 8) {
+      const float ui = ub[i];
+      const float* sr = Sb + (long long)i * M + c0 + lane;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        int j = c0 + lane + 32 * q;
+        if (j < M) {
           float z = __fsub_rn(__fadd_rn(__fadd_rn(sr[32 * q], ui), vj[q]), norm);
           if (z > m[q]) {
             m[q] = z;
@@ -258,7 +221,7 @@ __global__ void __launch_bounds__(256) sk_col_kernel(const float* __restrict__ S
       for (int w = 1; w < 8; w++) {
         float m2 = sm_m[w][threadIdx.x], s2 = sm_s[w][threadIdx.x];
         if (MODE == 0) {
-          lse_join(mm, ss, m2, s2);
+          lse_join<FAST>(mm, ss, m2, s2);
         } else {
           int i1 = __float_as_int(ss), i2 = __float_as_int(s2);
           if (m2 > mm || (m2 == mm && i2 < i1)) {
@@ -289,7 +252,7 @@ __global__ void __launch_bounds__(256) sk_col_kernel(const float* __restrict__ S
       for (int r = 1; r < R; r++) {
         float m2 = __ldcg(&p0[(long long)r * pstride + 2 * j]), s2 = __ldcg(&p0[(long long)r * pstride + 2 * j + 1]);
         if (MODE == 0) {
-          lse_join(mm, ss, m2, s2);
+          lse_join<FAST>(mm, ss, m2, s2);
         } else {
           int i1 = __float_as_int(ss), i2 = __float_as_int(s2);
           if (m2 > mm || (m2 == mm && i2 < i1)) {
@@ -299,7 +262,7 @@ __global__ void __launch_bounds__(256) sk_col_kernel(const float* __restrict__ S
         }
       }
       if (MODE == 0) {
-        lse_join(mm, ss, alpha + ub[N], 1.f);   // dustbin row
+        lse_join<FAST>(mm, ss, alpha + ub[N], 1.f);   // dustbin row
         out_v[(long long)b * (M + 1) + j] = norm - (mm + logf(ss));
       } else {
         int bidx = __float_as_int(ss);
@@ -311,11 +274,11 @@ __global__ void __launch_bounds__(256) sk_col_kernel(const float* __restrict__ S
   if (MODE == 0 && cb == 0) {
     // dustbin column: LSE_i(alpha + u_i), i = 0..N
     float mm = -INFINITY, ss = 0.f;
-    for (int i = threadIdx.x; i <= N; i += 256) lse_push(mm, ss, alpha + ub[i]);
+    for (int i = threadIdx.x; i <= N; i += 256) lse_push<FAST>(mm, ss, alpha + ub[i]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       float m2 = __shfl_xor_sync(0xffffffffu, mm, o), s2 = __shfl_xor_sync(0xffffffffu, ss, o);
-      lse_join(mm, ss, m2, s2);
+      lse_join<FAST>(mm, ss, m2, s2);
     }
     __syncthreads();
     if (lane == 0) {
@@ -324,7 +287,7 @@ __global__ void __launch_bounds__(256) sk_col_kernel(const float* __restrict__ S
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int w = 1; w < 8; w++) lse_join(mm, ss, sm_m[0][w], sm_s[0][w]);
+      for (int w = 1; w < 8; w++) lse_join<FAST>(mm, ss, sm_m[0][w], sm_s[0][w]);
       out_v[(long long)b * (M + 1) + M] = log_nu_bin - (mm + logf(ss));
     }
   }
@@ -525,24 +488,6 @@ int sg_frontend(const float* desc, long long desc_img_stride, int ldk, const flo
   return SFM_OK;
 }
 
-int col_stats_f32(const float* X, int ld, int C, int g0_rows, int g1_rows, float* mean, float* var,
-                  cudaStream_t st) {
-  dim3 grid(cdiv(C, 32), 2);
-  col_stats_kernel<<<grid, 256, 0, st>>>(X, ld, C, g0_rows, g1_rows, mean, var);
-  SFM_LAUNCH_CHECK();
-  return SFM_OK;
-}
-
-int bn_relu_f32(float* X, int ld, int C, int g0_rows, int g1_rows, const float* mean, const float* var,
-                const float* gamma, const float* beta, float eps, cudaStream_t st) {
-  SFM_REQUIRE(C % 4 == 0 && ld % 4 == 0, "bn_relu: C and ld must be multiples of 4");
-  long long total4 = (long long)(g0_rows + g1_rows) * (C / 4);
-  if (total4 == 0) return SFM_OK;
-  bn_relu_kernel<<<cdiv(total4, 256), 256, 0, st>>>(X, ld, C / 4, g0_rows, total4, mean, var, gamma, beta, eps);
-  SFM_LAUNCH_CHECK();
-  return SFM_OK;
-}
-
 int softmax_rows_f32(float* S, long long rows, int M, int ld, cudaStream_t st) {
   if (rows == 0 || M == 0) return SFM_OK;
   softmax_rows_kernel<<<cdiv(rows * 32, 256), 256, 0, st>>>(S, rows, M, ld);
@@ -550,9 +495,22 @@ int softmax_rows_f32(float* S, long long rows, int M, int ld, cudaStream_t st) {
   return SFM_OK;
 }
 
+// Pairs swept together per launch.  Measured on B200 (profiles/README.md): running all iterations on
+// L2-sized groups of 1/2/4 pairs is SLOWER than sweeping the whole batch (launch-latency bound,
+// 42 % / 29 % / 23 % vs 20 % of the step), so the default is the whole batch; SFM_SK_SUB overrides.
+int sinkhorn_sub_batch(int B, int N, int M) {
+  (void)N; (void)M;
+  int sub = B;
+  if (const char* e = getenv("SFM_SK_SUB")) sub = atoi(e);
+  if (sub < 1) sub = 1;
+  if (sub > B) sub = B;
+  return sub;
+}
+
 static int pick_R(int B, int N, int M) {
+  const int sub = sinkhorn_sub_batch(B, N, M);
   int colblocks = cdiv(M, 128);
-  long long base = (long long)B * colblocks;
+  long long base = (long long)sub * colblocks;
   int R = (int)((148 * 4 + base - 1) / base);
   int maxR = (N + 63) / 64;
   if (R > maxR) R = maxR;
@@ -579,14 +537,30 @@ int sinkhorn_run(const SinkhornArgs& a, cudaStream_t st) {
   fill_kernel<<<cdiv(nv, 256), 256, 0, st>>>(a.v, nv, 0.f);
   fill_kernel<<<cdiv(nu, 256), 256, 0, st>>>(a.u, nu, 0.f);
   SFM_LAUNCH_CHECK_N(2);
-  dim3 rgrid(cdiv(N + 1, 8), B);
-  dim3 cgrid(cdiv(M, 128), a.R, B);
-  for (int it = 0; it < a.iters; it++) {
-    sk_row_kernel<<<rgrid, 256, 0, st>>>(a.S, N, M, a.alpha, a.v, a.u, norm, log_mu_bin);
-    sk_col_kernel<0><<<cgrid, 256, 0, st>>>(a.S, N, M, a.alpha, a.u, nullptr, a.v, a.part, a.counters, a.R, norm,
-                                            log_nu_bin, nullptr, nullptr);
+  const int sub = sinkhorn_sub_batch(B, N, M);
+  for (int b0 = 0; b0 < B; b0 += sub) {
+    const int nb = (B - b0) < sub ? (B - b0) : sub;
+    const float* S = a.S + (long long)b0 * N * M;
+    float* u = a.u + (long long)b0 * (N + 1);
+    float* v = a.v + (long long)b0 * (M + 1);
+    float* part = a.part + (long long)b0 * a.R * (M + 1) * 2;
+    int* counters = a.counters + b0 * cdiv(M, 128);
+    dim3 rgrid(cdiv(N + 1, 8), nb);
+    dim3 cgrid(cdiv(M, 128), a.R, nb);
+    for (int it = 0; it < a.iters; it++) {
+      if (a.fast) {
+        sk_row_kernel<true><<<rgrid, 256, 0, st>>>(S, N, M, a.alpha, v, u, norm, log_mu_bin);
+        sk_col_kernel<0, true><<<cgrid, 256, 0, st>>>(S, N, M, a.alpha, u, nullptr, v, part, counters, a.R, norm,
+                                                      log_nu_bin, nullptr, nullptr);
+      } else {
+        sk_row_kernel<false><<<rgrid, 256, 0, st>>>(S, N, M, a.alpha, v, u, norm, log_mu_bin);
+        sk_col_kernel<0, false><<<cgrid, 256, 0, st>>>(S, N, M, a.alpha, u, nullptr, v, part, counters, a.R, norm,
+                                                       log_nu_bin, nullptr, nullptr);
+      }
+    }
+    count_launches(2 * a.iters);
   }
-  SFM_LAUNCH_CHECK_N(2 * a.iters);
+  SFM_CUDA(cudaGetLastError());
   return SFM_OK;
 }
 
@@ -597,7 +571,7 @@ int argmax_rows_cols(const SinkhornArgs& a, float norm, float* max0, int* idx0, 
   dim3 rgrid(cdiv(N, 8), B);
   sk_row_argmax_kernel<<<rgrid, 256, 0, st>>>(a.S, N, M, a.u, a.v, norm, max0, idx0);
   dim3 cgrid(cdiv(M, 128), a.R, B);
-  sk_col_kernel<1><<<cgrid, 256, 0, st>>>(a.S, N, M, a.alpha, a.u, a.v, nullptr, a.part, a.counters, a.R, norm, 0.f,
+  sk_col_kernel<1, false><<<cgrid, 256, 0, st>>>(a.S, N, M, a.alpha, a.u, a.v, nullptr, a.part, a.counters, a.R, norm, 0.f,
                                           max1, idx1);
   SFM_LAUNCH_CHECK_N(2);
   return SFM_OK;

@@ -14,13 +14,6 @@ int sg_frontend(const float* desc, long long desc_img_stride, int ldk, const flo
                 int kcap, const int* idx, int B, int K, int imgH, int imgW, float* X, float* kin,
                 cudaStream_t st);
 
-// per-channel batch statistics over token groups (train-mode BatchNorm1d, superglue.py:56-57)
-//   X [T, C] (ld), groups g: rows [gstart[g], gstart[g+1]);  mean/var: [G, C] (biased variance)
-int col_stats_f32(const float* X, int ld, int C, int g0_rows, int g1_rows, float* mean, float* var,
-                  cudaStream_t st);
-// X = relu((X - mean) * rsqrt(var + eps) * gamma + beta), in place, per group
-int bn_relu_f32(float* X, int ld, int C, int g0_rows, int g1_rows, const float* mean, const float* var,
-                const float* gamma, const float* beta, float eps, cudaStream_t st);
 // in-place softmax over the last dim of [rows, M] (ld)
 int softmax_rows_f32(float* S, long long rows, int M, int ld, cudaStream_t st);
 
@@ -35,6 +28,8 @@ struct SinkhornArgs {
   float* part;      // [B, R, M+1, 2] column partials
   int* counters;    // [B, colblocks] zero-initialised, self-resetting
   int R;            // row splits of the column pass
+  int sub_batch = 0;  // pairs per L2-resident sweep group (0 = auto)
+  bool fast = false;  // ex2.approx exponentials (bf16 precision mode) instead of IEEE expf
 };
 size_t sinkhorn_partial_floats(int B, int N, int M, int* R_out);
 size_t sinkhorn_counter_ints(int B, int M);

@@ -7,8 +7,9 @@
 //   warp 1    : tcgen05.mma issuer:  S_t = Q_t K_j^T  (SS, fp32 in TMEM),  O_t = P_t V_j  (A = P from TMEM)
 //   warps 2-5 : softmax warpgroup of tile 0 (thread = query row), warps 6-9: tile 1
 // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512)
-// The running output is kept in registers (64 fp32 per row); every K/V tile produces a fresh
-// P V partial in TMEM that the softmax threads fold in with the online-softmax rescale.
+// O accumulates in TMEM across K/V tiles.  The softmax threads keep a (possibly stale) reference
+// maximum per row and only rescale O / the running sum when the true maximum has grown by more
+// than 2^8 (lazy rescale: probabilities stay <= 256, exact after the final division by the sum).
 #include "tc_common.cuh"
 #include "tc_path.cuh"
 
@@ -95,12 +96,20 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);  // S = Q K^T : B = K tile, K-major
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);   // O = P V   : B = V tile, MN-major
+      uint64_t q_desc[2], k_desc[KV_STAGES], v_desc[KV_STAGES];
+#pragma unroll
+      for (int t = 0; t < 2; t++) q_desc[t] = umma_desc_sw128(smem_u32(sQ + t * TILE_BYTES), 16, 1024);
+#pragma unroll
+      for (int s = 0; s < KV_STAGES; s++) {
+        k_desc[s] = umma_desc_sw128(smem_u32(sK + s * TILE_BYTES), 16, 1024);
+        v_desc[s] = umma_desc_sw128(smem_u32(sV + s * TILE_BYTES), 1024, 1024);
+      }
       auto issue_s = [&](int t, int stage) {
-        const uint32_t a_addr = smem_u32(sQ + t * TILE_BYTES), b_addr = smem_u32(sK + stage * TILE_BYTES);
+        const uint64_t ad = q_desc[t], bd = stage == 0 ? k_desc[0] : (stage == 1 ? k_desc[1] : k_desc[2]);
 #pragma unroll
         for (int k = 0; k < 4; k++)
-          umma_ss(tmem + COL_S + t * 128, umma_desc_sw128(a_addr + k * 32, 16, 1024),
-                  umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc_s, k != 0);
+          umma_ss(tmem + COL_S + t * 128, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc_s,
+                  k != 0);
         umma_commit(&bars->s_full[t]);
       };
       mbar_wait(&bars->q_full, 0);
@@ -121,15 +130,11 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
             }
             issue_s(t, s1);
           }
-          if (j > 0) {
-            mbar_wait(&bars->o_free[t], (j - 1) & 1);  // softmax threads have folded O_t(j-1)
-            tc_fence_after();
-          }
-          const uint32_t v_addr = smem_u32(sV + s * TILE_BYTES);
+          const uint64_t vd = s == 0 ? v_desc[0] : (s == 1 ? v_desc[1] : v_desc[2]);
 #pragma unroll
           for (int k = 0; k < 8; k++)  // 16 keys per step: 16 V rows = 2048 bytes, P advances 8 columns
-            umma_ts(tmem + COL_O + t * 64, tmem + COL_P + t * 64 + k * 8,
-                    umma_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_o, k != 0);
+            umma_ts(tmem + COL_O + t * 64, tmem + COL_P + t * 64 + k * 8, umma_desc_advance(vd, k * 2048), idesc_o,
+                    (j | k) != 0);
           umma_commit(&bars->o_full[t]);
         }
         umma_commit(&bars->kv_empty[s]);
@@ -143,91 +148,92 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
     const int qi = qblk * 256 + t * 128 + row_in_tile;  // query index inside the pair
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     const float c = 0.125f * 1.4426950408889634f;  // log2(e) / sqrt(64)
-    float m_run = -INFINITY, l_run = 0.f;
-    float acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; i++) acc[i] = 0.f;
+    float m_used = -INFINITY, l_run = 0.f;
 
     for (int j = 0; j < n_kv; j++) {
       mbar_wait(&bars->s_full[t], j & 1);
       tc_fence_after();
       const int valid = min(128, Nk - j * 128);  // columns of this tile that are real keys
-      // pass 1: row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ch++) {
-        uint32_t r[32];
-        tmem_ld_32x32(lane_addr + COL_S + t * 128 + ch * 32, r);
-        tmem_wait_ld();
-        if (valid >= (ch + 1) * 32) {
+      uint32_t sv[128];
 #pragma unroll
-          for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
+      for (int ch = 0; ch < 4; ch++)
+        tmem_ld_32x32(lane_addr + COL_S + t * 128 + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[ch * 32]));
+      tmem_wait_ld();
+      if (valid < 128) {
 #pragma unroll
-          for (int i = 0; i < 32; i++)
-            if (ch * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
+        for (int i = 0; i < 128; i++)
+          if (i >= valid) sv[i] = 0xff800000u;  // -inf
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f((m_run - m_new) * c);
-      const float mc = m_new * c;
-      l_run *= alpha;
+      float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 64; i++) acc[i] *= alpha;
-      m_run = m_new;
-      // pass 2: probabilities -> bf16 P in TMEM
-      float lsum = 0.f;
-#pragma unroll 1
-      for (int half = 0; half < 2; half++) {
-        uint32_t pk[32];
+      for (int i = 0; i < 128; i++) mx = fmaxf(mx, __uint_as_float(sv[i]));
+      bool waited_o = false;
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool grow = (mx - m_used) * c > 8.0f;
+        if (__any_sync(0xffffffffu, grow)) {
+          // O_t must be quiescent: P V of the previous tile has completed
+          mbar_wait(&bars->o_full[t], (j - 1) & 1);
+          tc_fence_after();
+          waited_o = true;
+          const float alpha = grow ? fast_exp2((m_used - mx) * c) : 1.f;
+          if (grow) {
+            m_used = mx;
+            l_run *= alpha;
+          }
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
-          const int ch = half * 2 + q;
-          uint32_t r[32];
-          tmem_ld_32x32(lane_addr + COL_S + t * 128 + ch * 32, r);
-          tmem_wait_ld();
+          for (int ch = 0; ch < 2; ch++) {
+            uint32_t r[32];
+            tmem_ld_32x32(lane_addr + COL_O + t * 64 + ch * 32, r);
+            tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = exp2f(fmaf(__uint_as_float(r[i]), c, -mc));
-            float p1 = exp2f(fmaf(__uint_as_float(r[i + 1]), c, -mc));
-            if (ch * 32 + i >= valid) p0 = 0.f;
-            if (ch * 32 + i + 1 >= valid) p1 = 0.f;
-            lsum += p0 + p1;
-            pk[q * 16 + (i >> 1)] = pack_bf16(p0, p1);
+            for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st_32x32(lane_addr + COL_O + t * 64 + ch * 32, r);
           }
         }
-        tmem_st_32x32(lane_addr + COL_P + t * 64 + half * 32, pk);
       }
-      l_run += lsum;
+      const float mc = m_used * c;
+      float lsum0 = 0.f, lsum1 = 0.f;
+      uint32_t pk[64];
+#pragma unroll
+      for (int i = 0; i < 128; i += 2) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(sv[i]), c, -mc));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(sv[i + 1]), c, -mc));
+        lsum0 += p0;
+        lsum1 += p1;
+        pk[i >> 1] = pack_bf16(p0, p1);
+      }
+      l_run += lsum0 + lsum1;
+      if (j > 0 && !waited_o) {  // P V (j-1) must have consumed P_t before it is overwritten
+        mbar_wait(&bars->o_full[t], (j - 1) & 1);
+        tc_fence_after();
+      }
+      tmem_st_32x32(lane_addr + COL_P + t * 64, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+      tmem_st_32x32(lane_addr + COL_P + t * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full[t]);
-      // fold the P V partial of this tile
-      mbar_wait(&bars->o_full[t], j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int ch = 0; ch < 2; ch++) {
-        uint32_t r[32];
-        tmem_ld_32x32(lane_addr + COL_O + t * 64 + ch * 32, r);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; i++) acc[ch * 32 + i] += __uint_as_float(r[i]);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->o_free[t]);
     }
-    if (qi < Nq) {
-      const float inv = 1.f / l_run;
-      __nv_bfloat16* dst = p.out + (qrow + t * 128 + row_in_tile) * 256 + head * 64;
-      uint4* d4 = reinterpret_cast<uint4*>(dst);
+    mbar_wait(&bars->o_full[t], (n_kv - 1) & 1);
+    tc_fence_after();
+    {
+      uint32_t o[64];
+      tmem_ld_32x32(lane_addr + COL_O + t * 64, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+      tmem_ld_32x32(lane_addr + COL_O + t * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+      tmem_wait_ld();
+      if (qi < Nq) {
+        const float inv = 1.f / l_run;
+        __nv_bfloat16* dst = p.out + (qrow + t * 128 + row_in_tile) * 256 + head * 64;
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-      for (int i = 0; i < 8; i++)
-        d4[i] = make_uint4(pack_bf16(acc[8 * i] * inv, acc[8 * i + 1] * inv),
-                           pack_bf16(acc[8 * i + 2] * inv, acc[8 * i + 3] * inv),
-                           pack_bf16(acc[8 * i + 4] * inv, acc[8 * i + 5] * inv),
-                           pack_bf16(acc[8 * i + 6] * inv, acc[8 * i + 7] * inv));
+        for (int i = 0; i < 8; i++)
+          d4[i] = make_uint4(pack_bf16(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv),
+                             pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv),
+                             pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv),
+                             pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv));
+      }
     }
   }
   tc_fence_before();

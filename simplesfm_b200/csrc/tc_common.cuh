@@ -123,6 +123,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// The descriptor of a tile whose start address moves by `byte_off` (a multiple of 16 that does not carry
+// out of the 14-bit address field): only the low word changes.  Lets the single MMA-issuing thread
+// hoist the descriptor construction out of its inner loop.
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t byte_off) {
+  return desc + (uint64_t)(byte_off >> 4);
+}
+
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulation.
 //   [4,6) D format: 1 = F32   [7,10) A format: 1 = BF16   [10,13) B format: 1 = BF16
 //   [15] A major (0 = K)      [16] B major (0 = K, 1 = MN)
@@ -156,6 +163,12 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

