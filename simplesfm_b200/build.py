@@ -20,6 +20,7 @@ LIB = os.path.join(HERE, "libsfm_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", os.path.join(ROOT, "include")]
+NVCC_FLAGS += os.environ.get("SFM_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

@@ -249,7 +249,12 @@ int sfm_load_superglue(sfm_handle_t h, const float* packed, size_t n) {
       fold_bn(W, b, g, be, rm, rv, cout, cin_p, Wf, bf);
       SFM_TRY(upload(h, Wf, &w.kWf[i]));
       SFM_TRY(upload(h, bf, &w.kbf[i]));
+      if (i == 3) {
+        SFM_TRY(upload_bf16(h, W, &w.kW3_h));
+        SFM_TRY(upload_bf16(h, Wf, &w.kW3f_h));
+      }
     }
+    if (i == 4) SFM_TRY(upload_bf16(h, W, &w.kW4_h));
   }
   int perm[256];
   for (int c = 0; c < 256; c++) perm[c] = (c % 64) * 4 + c / 64;  // head-contiguous c' -> reference channel d*4+h

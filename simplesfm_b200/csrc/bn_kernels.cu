@@ -66,6 +66,59 @@ __global__ void __launch_bounds__(256) bn_partial_kernel(const T* __restrict__ X
   }
 }
 
+// bf16 fast path (C % 8 == 0, C <= 2048): one pass, 16-byte loads, thread = 8 consecutive channels,
+// 256 / (C/8) row lanes; (sum, sum of squares) in fp32 over <= RB rows -> (mean, centred M2).
+__global__ void __launch_bounds__(256) bn_partial_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ld, int C,
+                                                              BnGroups gr, int nb0, int nb1,
+                                                              float* __restrict__ partial) {
+  extern __shared__ float red[];  // [lanes][C][2]
+  const int blk = blockIdx.x;
+  const int side = blk >= gr.G * nb0 ? 1 : 0;
+  const int local = side ? blk - gr.G * nb0 : blk;
+  const int nb = side ? nb1 : nb0;
+  const int grp = local / nb, bi = local % nb;
+  const long long rows_g = (side ? gr.T1 : gr.T0) / gr.G;
+  const long long base = (side ? gr.T0 : 0) + grp * rows_g;
+  const long long r0 = base + (long long)bi * RB;
+  const int rows = (int)min((long long)RB, base + rows_g - r0);
+  const int tpr = C / 8;             // threads per row
+  const int lanes = 256 / tpr;       // row lanes
+  const int cl = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  float s[8], q[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) s[k] = q[k] = 0.f;
+  if (rl < lanes) {
+    const uint4* src = reinterpret_cast<const uint4*>(X + r0 * ld + cl * 8);
+    const int ld16 = ld / 8;
+    for (int r = rl; r < rows; r += lanes) {
+      uint4 raw = src[(long long)r * ld16];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        float2 v = __bfloat1622float2(h[k]);
+        s[2 * k] += v.x; s[2 * k + 1] += v.y;
+        q[2 * k] = fmaf(v.x, v.x, q[2 * k]); q[2 * k + 1] = fmaf(v.y, v.y, q[2 * k + 1]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      red[(rl * C + cl * 8 + k) * 2] = s[k];
+      red[(rl * C + cl * 8 + k) * 2 + 1] = q[k];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float ts = 0.f, tq = 0.f;
+    for (int l = 0; l < lanes; l++) {
+      ts += red[(l * C + c) * 2];
+      tq += red[(l * C + c) * 2 + 1];
+    }
+    const float mu = ts / (float)rows;
+    partial[((long long)blk * C + c) * 2] = mu;
+    partial[((long long)blk * C + c) * 2 + 1] = fmaxf(tq - ts * mu, 0.f);
+  }
+}
+
 // Chan's pairwise combination of the block moments (fixed tree => deterministic), one warp per
 // (group, channel); then scale = gamma / sqrt(var + eps), shift = beta - mean * scale.
 __device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float mb, float qb) {
@@ -158,6 +211,21 @@ __global__ void bn_apply_bf16_kernel(uint4* __restrict__ X, int ld8, int C8, BnG
   X[row * ld8 + c8] = raw;
 }
 
+__global__ void bn_apply_f32_to_bf16_kernel(const float4* __restrict__ X, int ld4, uint2* __restrict__ out, int ldo4,
+                                            int C4, BnGroups gr, long long total4, const float4* __restrict__ scale,
+                                            const float4* __restrict__ shift) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = i % C4;
+  const long long row = i / C4;
+  const int g = group_of(gr, row);
+  const float4 x = X[row * ld4 + c4];
+  const float4 a = scale[g * C4 + c4], b = shift[g * C4 + c4];
+  __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(fmaf(x.x, a.x, b.x), 0.f), fmaxf(fmaf(x.y, a.y, b.y), 0.f));
+  __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(fmaf(x.z, a.z, b.z), 0.f), fmaxf(fmaf(x.w, a.w, b.w), 0.f));
+  out[row * ldo4 + c4] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
 }  // namespace
 
 static int blocks_per_group(long long rows_total, int G) { return cdiv(rows_total / G, RB); }
@@ -172,7 +240,13 @@ int bn_train_stats(const T* X, int ld, int C, const BnGroups& g, const float* ga
   const int nb0 = blocks_per_group(g.T0, g.G), nb1 = blocks_per_group(g.T1, g.G);
   const int total = g.G * (nb0 + nb1);
   if (total == 0) return SFM_OK;
-  bn_partial_kernel<T><<<total, 256, 0, st>>>(X, ld, C, g, nb0, nb1, partial);
+  if (sizeof(T) == 2 && C % 8 == 0 && 256 % (C / 8) == 0 && ld % 8 == 0) {
+    const int lanes = 256 / (C / 8);
+    bn_partial_bf16_kernel<<<total, 256, (size_t)lanes * C * 2 * sizeof(float), st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(X), ld, C, g, nb0, nb1, partial);
+  } else {
+    bn_partial_kernel<T><<<total, 256, 0, st>>>(X, ld, C, g, nb0, nb1, partial);
+  }
   bn_final_kernel<<<dim3(cdiv(C, 8), 2 * g.G), 256, 0, st>>>(partial, C, g, nb0, nb1, gamma, beta, eps, scale, shift);
   SFM_LAUNCH_CHECK_N(2);
   return SFM_OK;
@@ -200,6 +274,19 @@ int bn_apply_relu<__nv_bfloat16>(__nv_bfloat16* X, int ld, int C, const BnGroups
   bn_apply_bf16_kernel<<<cdiv(total, 256), 256, 0, st>>>(reinterpret_cast<uint4*>(X), ld / 8, C / 8, g, total,
                                                          reinterpret_cast<const float4*>(scale),
                                                          reinterpret_cast<const float4*>(shift));
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+int bn_apply_relu_f32_to_bf16(const float* X, int ld, __nv_bfloat16* out, int ld_out, int C, const BnGroups& g,
+                              const float* scale, const float* shift, cudaStream_t st) {
+  SFM_REQUIRE(C % 4 == 0 && ld % 4 == 0 && ld_out % 4 == 0, "bn_apply_relu_f32_to_bf16: C, ld must be multiples of 4");
+  const long long total = (g.T0 + g.T1) * (C / 4);
+  if (total == 0) return SFM_OK;
+  bn_apply_f32_to_bf16_kernel<<<cdiv(total, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(X), ld / 4,
+                                                                reinterpret_cast<uint2*>(out), ld_out / 4, C / 4, g,
+                                                                total, reinterpret_cast<const float4*>(scale),
+                                                                reinterpret_cast<const float4*>(shift));
   SFM_LAUNCH_CHECK();
   return SFM_OK;
 }

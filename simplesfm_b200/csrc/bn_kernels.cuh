@@ -22,4 +22,8 @@ int bn_train_stats(const T* X, int ld, int C, const BnGroups& g, const float* ga
 template <typename T>
 int bn_apply_relu(T* X, int ld, int C, const BnGroups& g, const float* scale, const float* shift, cudaStream_t st);
 
+// out (bf16, ld_out) = relu(X (f32, ld) * scale + shift): hands a fp32 layer to the tensor-core path
+int bn_apply_relu_f32_to_bf16(const float* X, int ld, __nv_bfloat16* out, int ld_out, int C, const BnGroups& g,
+                              const float* scale, const float* shift, cudaStream_t st);
+
 }  // namespace sfm

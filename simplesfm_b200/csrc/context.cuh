@@ -41,6 +41,7 @@ struct SgWeights {
   float* kW[5];
   float* kb[5];
   SgBn kbn[4];
+  __nv_bfloat16 *kW3_h, *kW3f_h, *kW4_h;  // bf16 copies of the two wide encoder layers (tensor-core path)
   float* kWf[4];  // eval-folded
   float* kbf[4];
   SgLayer L[18];

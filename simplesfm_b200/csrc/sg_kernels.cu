@@ -511,7 +511,7 @@ static int pick_R(int B, int N, int M) {
   const int sub = sinkhorn_sub_batch(B, N, M);
   int colblocks = cdiv(M, 128);
   long long base = (long long)sub * colblocks;
-  int R = (int)((148 * 4 + base - 1) / base);
+  int R = (int)((148 * 16 + base - 1) / base);   // >= 16 CTAs per SM in flight + queued: balances the tail
   int maxR = (N + 63) / 64;
   if (R > maxR) R = maxR;
   if (R < 1) R = 1;

@@ -164,53 +164,65 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
         for (int i = 0; i < 128; i++)
           if (i >= valid) sv[i] = 0xff800000u;  // -inf
       }
-      float mx = -INFINITY;
+      // 8 independent chains (a single 128-long FMNMX dependency chain is latency-bound with 2 warps/SMSP)
+      float mxa[8];
 #pragma unroll
-      for (int i = 0; i < 128; i++) mx = fmaxf(mx, __uint_as_float(sv[i]));
-      bool waited_o = false;
+      for (int q = 0; q < 8; q++) mxa[q] = __uint_as_float(sv[q]);
+#pragma unroll
+      for (int i = 8; i < 128; i += 8)
+#pragma unroll
+        for (int q = 0; q < 8; q++) mxa[q] = fmaxf(mxa[q], __uint_as_float(sv[i + q]));
+      const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
+                             fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+      // lazy rescale decision (the O rescale itself is deferred until S has been consumed, so that
+      // the 128 S registers and the O staging registers are never live together)
+      float alpha = 1.f;
+      bool grow = false;
       if (j == 0) {
         m_used = mx;
       } else {
-        const bool grow = (mx - m_used) * c > 8.0f;
-        if (__any_sync(0xffffffffu, grow)) {
-          // O_t must be quiescent: P V of the previous tile has completed
-          mbar_wait(&bars->o_full[t], (j - 1) & 1);
-          tc_fence_after();
-          waited_o = true;
-          const float alpha = grow ? fast_exp2((m_used - mx) * c) : 1.f;
-          if (grow) {
-            m_used = mx;
-            l_run *= alpha;
-          }
-#pragma unroll
-          for (int ch = 0; ch < 2; ch++) {
-            uint32_t r[32];
-            tmem_ld_32x32(lane_addr + COL_O + t * 64 + ch * 32, r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st_32x32(lane_addr + COL_O + t * 64 + ch * 32, r);
-          }
+        grow = (mx - m_used) * c > 8.0f;
+        if (grow) {
+          alpha = fast_exp2((m_used - mx) * c);
+          m_used = mx;
+          l_run *= alpha;
         }
       }
+      const bool any_grow = __any_sync(0xffffffffu, grow);
       const float mc = m_used * c;
-      float lsum0 = 0.f, lsum1 = 0.f;
-      uint32_t pk[64];
-#pragma unroll
-      for (int i = 0; i < 128; i += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(sv[i]), c, -mc));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(sv[i + 1]), c, -mc));
-        lsum0 += p0;
-        lsum1 += p1;
-        pk[i >> 1] = pack_bf16(p0, p1);
-      }
-      l_run += lsum0 + lsum1;
-      if (j > 0 && !waited_o) {  // P V (j-1) must have consumed P_t before it is overwritten
+      if (j > 0) {  // P V (j-1) must have consumed P_t before it is overwritten (and O_t must be quiescent)
         mbar_wait(&bars->o_full[t], (j - 1) & 1);
         tc_fence_after();
       }
-      tmem_st_32x32(lane_addr + COL_P + t * 64, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
-      tmem_st_32x32(lane_addr + COL_P + t * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int half = 0; half < 2; half++) {   // two 64-key halves keep the packed-P registers short-lived
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          const int e = half * 64 + i;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), c, -mc));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), c, -mc));
+          const float p2 = fast_exp2(fmaf(__uint_as_float(sv[e + 2]), c, -mc));
+          const float p3 = fast_exp2(fmaf(__uint_as_float(sv[e + 3]), c, -mc));
+          ls[0] += p0; ls[1] += p1; ls[2] += p2; ls[3] += p3;
+          pk[i >> 1] = pack_bf16(p0, p1);
+          pk[(i >> 1) + 1] = pack_bf16(p2, p3);
+        }
+        tmem_st_32x32(lane_addr + COL_P + t * 64 + half * 32, pk);
+      }
+      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      if (any_grow) {   // warp-uniform: rescale the running output of rows whose reference maximum moved
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+          uint32_t r[32];
+          tmem_ld_32x32(lane_addr + COL_O + t * 64 + ch * 32, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st_32x32(lane_addr + COL_O + t * 64 + ch * 32, r);
+        }
+      }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();

@@ -42,6 +42,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -135,9 +143,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0);
       int stage = 0, phase = 0, wphase = 0, tile = 0;
       // descriptors of every A stage / W k-block are loop invariants: build them once
-      uint64_t a_desc[STAGES], w_desc[KBLOCKS];
-#pragma unroll
-      for (int s = 0; s < STAGES; s++) a_desc[s] = umma_desc_sw128(smem_u32(sA + s * A_STAGE_BYTES), 16, 1024);
+      uint64_t w_desc[KBLOCKS];
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA), 16, 1024);  // stage s: + s * A_STAGE_BYTES
 #pragma unroll
       for (int kb = 0; kb < KBLOCKS; kb++) w_desc[kb] = umma_desc_sw128(smem_u32(sW + kb * BN * 128), 16, 1024);
       for (int pj = slot; pj < n_pj; pj += n_slots) {
@@ -153,8 +160,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int kb = 0; kb < KBLOCKS; kb++) {
             DBG_WAIT(0, mbar_wait(&bars->a_full[stage], phase));
             tc_fence_after();
-            // STAGES divides KBLOCKS, so the stage index of k-block kb is the compile-time kb % STAGES
-            const uint64_t ad = a_desc[kb % STAGES], bd = w_desc[kb];
+            const uint64_t ad = umma_desc_advance(a_desc0, stage * A_STAGE_BYTES), bd = w_desc[kb];
 #pragma unroll
             for (int k = 0; k < BK / 16; k++)
               umma_ss(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, (kb | k) != 0);
@@ -175,6 +181,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int wg = (warp - 2) >> 2;   // 0/1: which half of the columns
     const int wg_tid = (warp - 2 - wg * 4) * 32 + lane;
     uint8_t* slab = sO + wg * SLAB_BYTES;
+    const uint32_t slab_u32 = smem_u32(slab);
     const int row_in_tile = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     int tile = 0;
@@ -211,6 +218,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (p.relu) x = fmaxf(x, 0.f);
             v[j] = x;
           }
+          if (p.accumulate_f && p.coalesced_rmw) {
+            // residual update X += delta through a fp32 slab so that the global read-modify-write of the
+            // fp32 master and the bf16 shadow store are full-line coalesced (4 rows x 128 B per warp op)
+            named_bar_sync(2 + wg, 128);  // previous chunk's readers are done with the slab
+            const uint32_t rowa = slab_u32 + row_in_tile * 128;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              sts128(rowa + ((j ^ (row_in_tile & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                     __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+            named_bar_sync(2 + wg, 128);
+            const int rsub = wg_tid >> 3, ch = wg_tid & 7;
+            float4 old[8];
+            const long long grow0 = (long long)mt * BM;
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+              const int r = it * 16 + rsub;
+              old[it] = (grow0 + r < p.M)
+                            ? *reinterpret_cast<const float4*>(p.out_f + (grow0 + r) * p.out_f_ld + n0 + ch * 4)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+              const int r = it * 16 + rsub;
+              const float4 d = lds128(slab_u32 + r * 128 + ((ch ^ (r & 7)) << 4));
+              float4 o = make_float4(old[it].x + d.x, old[it].y + d.y, old[it].z + d.z, old[it].w + d.w);
+              if (grow0 + r < p.M) {
+                *reinterpret_cast<float4*>(p.out_f + (grow0 + r) * p.out_f_ld + n0 + ch * 4) = o;
+                if (p.out_h != nullptr)
+                  *reinterpret_cast<uint2*>(p.out_h + (grow0 + r) * p.out_h_ld + n0 + ch * 4) =
+                      make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+              }
+            }
+            continue;
+          }
           if (of != nullptr && row_ok && n0 < p.N) {
             const bool full = n0 + 32 <= p.N;
             if (full && p.vec_f) {
@@ -226,13 +267,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 dst[j] = o;
               }
             } else {
-              for (int j = 0; j < 32 && n0 + j < p.N; j++) {
-                float o = v[j];
-                if (p.accumulate_f) {
-                  o += of[n0 + j];
-                  v[j] = o;
+#pragma unroll
+              for (int j = 0; j < 32; j++) {   // predicated, fully unrolled: keeps v[] in registers
+                if (n0 + j < p.N) {
+                  float o = v[j];
+                  if (p.accumulate_f) {
+                    o += of[n0 + j];
+                    v[j] = o;
+                  }
+                  of[n0 + j] = o;
                 }
-                of[n0 + j] = o;
               }
             }
           }
@@ -242,13 +286,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               DBG_WAIT(1, if (wg_tid == 0) tma_store_wait_read());  // previous store has finished reading the slab
               if (!(p.dbg_flags & 8)) { DBG_WAIT(2, named_bar_sync(2 + wg, 128)); }
             }
-            uint8_t* rowp = slab + row_in_tile * 128;
+            const uint32_t rowa = slab_u32 + row_in_tile * 128;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
               const int chunk = (c & 1) * 4 + j;
-              *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row_in_tile & 7)) << 4)) =
-                  make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                             pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+              sts128(rowa + ((chunk ^ (row_in_tile & 7)) << 4), pack_bf16(v[8 * j], v[8 * j + 1]),
+                     pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
+                     pack_bf16(v[8 * j + 6], v[8 * j + 7]));
             }
             if ((c & 1) == 1 || NCH == 1) {
               if (!(p.dbg_flags & 16)) { DBG_WAIT(1, fence_proxy_async()); }
@@ -363,7 +407,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
 }
 
 int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
-  SFM_REQUIRE(p.K == 256 || p.K == 512, "tc_gemm: K must be 256 or 512 (got %d)", p.K);
+  SFM_REQUIRE(p.K == 128 || p.K == 256 || p.K == 512, "tc_gemm: K must be 128, 256 or 512 (got %d)", p.K);
   SFM_REQUIRE(p.M > 0 && p.N > 0 && p.batch > 0, "tc_gemm: bad dims");
   SFM_REQUIRE(p.K1 % 64 == 0 && p.K1 > 0 && p.K1 <= p.K, "tc_gemm: bad split point");
   SFM_REQUIRE(p.out_h == nullptr || (p.out_h_ld % 8 == 0 && p.batch == 1 && p.M == p.a_rows),
@@ -374,7 +418,7 @@ int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
     SFM_TRY(make_tmap_bf16(&mA2, p.A2, p.a_rows, p.K - p.K1, p.lda2, BM));
   else
     mA2 = mA;
-  const bool wide = (p.K == 256) && (p.N > 128);
+  const bool wide = (p.K <= 256) && (p.N > 128);
   SFM_TRY(make_tmap_bf16(&mW, p.W, p.w_rows, p.K, p.ldw, wide ? 256 : 128));
   // output map: rows beyond M and columns beyond N are clipped by the TMA unit
   if (p.out_h != nullptr)
@@ -384,6 +428,12 @@ int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
   TcGemm q = p;
   q.vec_f = (p.out_f != nullptr) && (p.out_f_ld % 4 == 0) && (p.out_f_bstride % 4 == 0) &&
             ((reinterpret_cast<uintptr_t>(p.out_f) & 15) == 0);
+  q.coalesced_rmw = p.accumulate_f && q.vec_f && p.batch == 1 && (p.N % 32 == 0) &&
+                    (p.out_h == nullptr || p.out_h_ld % 4 == 0);
+  if (p.K == 128) {
+    if (wide) return launch<256, 2>(q, mA, mA2, mW, mO, num_sms, st);
+    return launch<128, 2>(q, mA, mA2, mW, mO, num_sms, st);
+  }
   if (p.K == 256) {
     if (wide) return launch<256, 4>(q, mA, mA2, mW, mO, num_sms, st);
     return launch<128, 4>(q, mA, mA2, mW, mO, num_sms, st);

@@ -24,11 +24,6 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
   const long long T0 = (long long)c.B * c.K0, T1 = (long long)c.B * c.K1, T = T0 + T1;
   const bool train = c.bn_mode == 0;
   const int sms = h->sm_count;
-  {
-    ProfScope ps(h, SFM_PROF_OTHER, st);
-    SFM_TRY(kenc_forward_f32(h, c, X, kin, b.t0, b.t1, b.bn_part, b.bn_scale, b.bn_shift, st));
-    SFM_TRY(f32_to_bf16(X, b.xh, T * 256, st));
-  }
   auto linear = [&](const __nv_bfloat16* A, int lda, const __nv_bfloat16* A2, int lda2, int K, int K1,
                     const __nv_bfloat16* W, int N, const float* bias, int relu, __nv_bfloat16* out_h, int ldo,
                     float* out_f, int accumulate) {
@@ -42,6 +37,51 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
     g.out_f = out_f; g.out_f_ld = 256; g.accumulate_f = accumulate;
     return tc_gemm(g, sms, st);
   };
+  {
+    // ---- keypoint encoder (superglue.py:72-82): 3->32->64->128 on the fp32 FFMA GEMM (keypoint coordinates
+    // stay fp32), the two wide layers 128->256->256 on tcgen05; the last layer accumulates straight into the
+    // fp32 residual stream X and emits its bf16 shadow.
+    ProfScope ps(h, SFM_PROF_OTHER, st);
+    const BnGroups gr{T0, T1, c.groups > 0 ? c.groups : 1};
+    const float* cur = kin;
+    int ld = 4;
+    float* pp[2] = {b.t0, b.t1};
+    __nv_bfloat16* a3 = b.hid;                  // [T,128] bf16 input of layer 3 (borrow the MLP hidden buffer)
+    __nv_bfloat16* a4 = b.hid + T * 128;        // [T,256] bf16 input of layer 4
+    for (int i = 0; i < 3; i++) {
+      const int cin = w.kch[i], cout = w.kch[i + 1];
+      float* out = pp[i & 1];
+      if (train) {
+        SFM_TRY(linear_f32_raw(cur, ld, nullptr, 0, 0, w.kW[i], cin, cout, w.kb[i], out, cout, T, 0, st));
+        SFM_TRY(bn_train_stats<float>(out, cout, cout, gr, w.kbn[i].gamma, w.kbn[i].beta, 1e-5f, b.bn_part, b.bn_scale,
+                                      b.bn_shift, st));
+        if (i < 2)
+          SFM_TRY(bn_apply_relu<float>(out, cout, cout, gr, b.bn_scale, b.bn_shift, st));
+        else
+          SFM_TRY(bn_apply_relu_f32_to_bf16(out, cout, a3, 128, cout, gr, b.bn_scale, b.bn_shift, st));
+      } else {
+        SFM_TRY(linear_f32_raw(cur, ld, nullptr, 0, 0, w.kWf[i], cin, cout, w.kbf[i], out, cout, T, GEMM_RELU, st));
+        if (i == 2) SFM_TRY(f32_to_bf16(out, a3, T * 128, st));
+      }
+      cur = out;
+      ld = cout;
+    }
+    TcGemm g3;
+    g3.A = a3; g3.lda = 128; g3.a_rows = T; g3.W = train ? w.kW3_h : w.kW3f_h; g3.ldw = 128; g3.w_rows = 256;
+    g3.M = (int)T; g3.N = 256; g3.K = 128; g3.K1 = 128; g3.bias = train ? w.kb[3] : w.kbf[3]; g3.relu = train ? 0 : 1;
+    g3.out_h = a4; g3.out_h_ld = 256;
+    SFM_TRY(tc_gemm(g3, sms, st));
+    if (train) {
+      SFM_TRY(bn_train_stats<__nv_bfloat16>(a4, 256, 256, gr, w.kbn[3].gamma, w.kbn[3].beta, 1e-5f, b.bn_part,
+                                            b.bn_scale, b.bn_shift, st));
+      SFM_TRY(bn_apply_relu<__nv_bfloat16>(a4, 256, 256, gr, b.bn_scale, b.bn_shift, st));
+    }
+    TcGemm g4;
+    g4.A = a4; g4.lda = 256; g4.a_rows = T; g4.W = w.kW4_h; g4.ldw = 256; g4.w_rows = 256;
+    g4.M = (int)T; g4.N = 256; g4.K = 256; g4.K1 = 256; g4.bias = w.kb[4];
+    g4.out_h = b.xh; g4.out_h_ld = 256; g4.out_f = X; g4.out_f_ld = 256; g4.accumulate_f = 1;
+    SFM_TRY(tc_gemm(g4, sms, st));
+  }
   for (int l = 0; l < 18; l++) {
     const SgLayer& L = w.L[l];
     const bool cross = l & 1;

@@ -17,6 +17,10 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
 int kenc_forward_f32(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float* t0, float* t1, float* part,
                      float* scale, float* shift, cudaStream_t st);
 
+// C = A W^T + b on the fp32 FFMA GEMM (sg_forward.cu)
+int linear_f32_raw(const float* A, int lda, const float* A2, int lda2, int K1, const float* W, int K, int N,
+                   const float* bias, float* C, int ldc, long long T, int flags, cudaStream_t st);
+
 namespace tc {
 
 // D_b[M,N] = alpha * A_b[M,K] * W_b[N,K]^T + bias   (bf16 operands, fp32 accumulation in TMEM)
@@ -40,7 +44,7 @@ struct TcGemm {
   long long out_f_ld = 0, out_f_bstride = 0;
   int accumulate_f = 0;  // out_f += result (residual stream); out_h then holds bf16(out_f)
   // filled by the launcher
-  int vec_f = 0, num_panels = 0, num_m_tiles = 0, cpp = 1;
+  int vec_f = 0, coalesced_rmw = 0, num_panels = 0, num_m_tiles = 0, cpp = 1;
   int dbg_flags = 0;
   long long* dbg = nullptr;  // optional per-role wait-cycle counters (SFM_TC_DEBUG)
 };

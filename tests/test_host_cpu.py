@@ -1,0 +1,169 @@
+"""CPU tests: the C-ABI library loads and exports every symbol of include/sfm_b200.h (no compute
+without a GPU), weight packing is strict, host-side Matcher logic (pair lists, shard ranges) and the
+multi-process gather run under gloo with world_size 2."""
+import ctypes as C
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_header_symbols():
+    from simplesfm_b200 import _lib
+    lib = _lib.lib()
+    syms = _lib.header_symbols()
+    assert len(syms) >= 25 and len(set(syms)) == len(syms)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/sfm_b200.h but not exported"
+    assert sorted(syms) == sorted(_lib._SIGNATURES), "ctypes signature table out of sync with the header"
+    assert lib.sfm_abi_version() == 1
+    assert lib.sfm_superpoint_packed_floats() == 1300865
+    assert lib.sfm_superglue_packed_floats() == 12042689
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never fall back."""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from simplesfm_b200 import _lib, synthetic
+    from simplesfm_b200.models.superglue import SuperGlue
+    from simplesfm_b200.models.superpoint import SuperPoint
+    h = C.c_void_p()
+    assert _lib.lib().sfm_create(0, C.byref(h)) != 0
+    assert b"no CPU fallback" in _lib.lib().sfm_last_error()
+    with pytest.raises(_lib.SfmError):
+        SuperPoint(synthetic.superpoint_state_dict(0))
+    with pytest.raises(_lib.SfmError):
+        SuperGlue(synthetic.superglue_state_dict(0))
+
+
+def test_workspace_queries_are_shape_functions():
+    from simplesfm_b200 import _lib
+    L = _lib.lib()
+    a = L.sfm_superglue_workspace_bytes(5, 2048, 2048, 1, 1)
+    b = L.sfm_superglue_workspace_bytes(40, 2048, 2048, 1, 8)
+    assert 0 < a < b
+    assert L.sfm_superglue_workspace_bytes(5, 2048, 2048, 0, 1) > a          # fp32 path materialises attention
+    assert L.sfm_superglue_workspace_bytes(5, 0, 10, 0, 1) == 0               # invalid shape -> 0 + error text
+    assert b"K0, K1 > 0" in L.sfm_last_error()
+    assert L.sfm_superpoint_workspace_bytes(1, 480, 640, 0) > 2 * 480 * 640 * 64 * 4
+    assert L.sfm_superpoint_workspace_bytes(1, 481, 640, 0) == 0
+    assert L.sfm_sinkhorn_workspace_bytes(2, 100, 90) > 0
+
+
+def test_weight_packing_strict(sp_weights, sg_weights):
+    from simplesfm_b200 import weights
+    p = weights.pack_superpoint(sp_weights)
+    assert p.numel() == 1300865 and p.dtype == torch.float32
+    assert torch.equal(p[:576], sp_weights["conv1a.weight"].reshape(-1))
+    q = weights.pack_superglue(sg_weights)
+    assert q.numel() == 12042689 and float(q[0]) == float(sg_weights["bin_score"])
+    assert len(weights.superglue_keys()) == 339 and len(weights.superpoint_keys()) == 24
+    bad = dict(sg_weights)
+    bad.pop("final_proj.bias")
+    with pytest.raises(RuntimeError):
+        weights.pack_superglue(bad)
+    bad = dict(sp_weights)
+    bad["extra.weight"] = torch.zeros(1)
+    with pytest.raises(RuntimeError):
+        weights.pack_superpoint(bad)
+
+
+def test_shard_ranges_cover_and_align():
+    from simplesfm_b200.distributed import image_block, shard_range
+    for n, chunk, world in ((1225, 5, 8), (1225, 5, 3), (7, 4, 2), (0, 5, 4), (499500, 5, 8), (3, 5, 8)):
+        spans = [shard_range(n, chunk, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        for (a, b), (c, d) in zip(spans, spans[1:]):
+            assert b == c and a <= b
+        for a, b in spans:
+            assert a % chunk == 0 or a == n           # chunk aligned => identical chunk composition
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= chunk
+    blocks = [image_block(50, r, 8) for r in range(8)]
+    assert blocks[0][0] == 0 and blocks[-1][1] == 50 and all(b == c for (_, b), (c, _) in zip(blocks, blocks[1:]))
+
+
+def test_install_as_simple_sfm_aliases():
+    import simplesfm_b200
+    simplesfm_b200.install_as_simple_sfm()
+    from simple_sfm.matchers import Matcher
+    from simple_sfm.matchers.matcher import Frame
+    from simple_sfm.models.superglue import SuperGlue, log_optimal_transport
+    from simple_sfm.models.superpoint import SuperPoint, simple_nms
+    import simplesfm_b200.matchers.matcher as mm
+    assert Matcher is mm.Matcher and Frame is mm.Frame
+    assert Frame._fields == ("descriptors", "keypoints_poses", "scores", "image")
+    import inspect
+    params = list(inspect.signature(Matcher.__init__).parameters)
+    assert params[1:9] == ["super_point_extractor_weights_path", "nms_radius", "keypoint_threshold", "matcher_type",
+                           "super_glue_weights_path", "match_threshold", "sinkhorn_iterations", "super_glue_batch"]
+    d = inspect.signature(Matcher.__init__).parameters
+    assert (d["matcher_type"].default, d["match_threshold"].default, d["sinkhorn_iterations"].default,
+            d["super_glue_batch"].default) == ("simple", 0.4, 20, 5)
+    s = inspect.signature(SuperGlue.__init__).parameters
+    assert (s["sinkhorn_iterations"].default, s["match_threshold"].default) == (100, 0.2)
+    p = inspect.signature(SuperPoint.__init__).parameters
+    assert (p["nms_radius"].default, p["keypoint_threshold"].default, p["max_keypoints"].default,
+            p["remove_borders"].default) == (4, 0.005, -1, 4)
+    for k in ("simple_sfm.matchers", "simple_sfm.matchers.matcher", "simple_sfm.matchers.simple_matcher",
+              "simple_sfm.models.superpoint", "simple_sfm.models.superglue", "simple_sfm.models", "simple_sfm"):
+        sys.modules.pop(k, None)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from simplesfm_b200.distributed import allgather_feature_records, gather_match_tables, image_block, shard_range
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        ids = list(range(1, 8))
+        pairs = np.array([(a, b) for i, a in enumerate(ids) for b in ids[i + 1:]])
+        lo, hi = shard_range(len(pairs), 4, rank, world)
+        rng = np.random.RandomState(0)
+        full = {(np.int64(a), np.int64(b)): rng.randint(0, 500, size=(int(a * 3 + b) % 9, 2)).astype(np.uint32)
+                for a, b in pairs}
+        local = {k: full[k] for k in list(full)[lo:hi]}
+        merged = gather_match_tables(local, pairs)
+        ok = list(merged.keys()) == list(full.keys()) and all(np.array_equal(merged[k], full[k]) and
+                                                              merged[k].dtype == np.uint32 for k in full)
+        # feature records: each rank owns a block of images
+        n_img, kcap = 5, 6
+        g = torch.Generator().manual_seed(1)
+        desc = torch.randn(n_img, 256, kcap, generator=g)
+        kp = torch.randn(n_img, kcap, 2, generator=g)
+        sc = torch.rand(n_img, kcap, generator=g)
+        cnt = torch.arange(n_img, dtype=torch.int32) + 1
+        a, b = image_block(n_img, rank, world)
+        d2, k2, s2, c2 = allgather_feature_records(desc[a:b], kp[a:b], sc[a:b], cnt[a:b], n_img)
+        ok = ok and torch.equal(d2, desc) and torch.equal(k2, kp) and torch.equal(s2, sc) and torch.equal(c2, cnt)
+        out.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_gather_tables_and_features():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
