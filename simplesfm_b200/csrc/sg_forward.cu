@@ -12,7 +12,7 @@ namespace sfm {
 namespace {
 
 struct SgBuffers {
-  float *X, *xk, *kin, *t0, *t1, *qkv, *msgp, *msg, *hid, *att, *bn_part, *bn_scale, *bn_shift, *md, *scores, *u, *v, *part, *max0, *max1;
+  float *X, *xk, *kin, *t0, *t1, *qkv, *msgp, *msg, *hid, *att, *bn_part, *bn_scale, *bn_shift, *md, *sk_fused, *sk_kb, *scores, *u, *v, *part, *max0, *max1;
   int *counters, *idx0, *idx1;
   int R, ldS;
 };
@@ -43,6 +43,8 @@ int carve(Arena& a, const SgCall& c, SgBuffers& b) {
   b.v = a.get<float>((size_t)c.B * (c.K1 + 1));
   b.part = a.get<float>(sinkhorn_partial_floats(c.B, c.K0, c.K1, &b.R));
   b.counters = a.get<int>(sinkhorn_counter_ints(c.B, c.K1));
+  b.sk_fused = c.precision == 1 ? a.get<float>(sinkhorn_fused_floats(c.B, c.K0, c.K1)) : nullptr;
+  b.sk_kb = c.precision == 1 ? a.get<float>((size_t)c.B * c.K0) : nullptr;
   b.max0 = a.get<float>((size_t)c.B * c.K0);
   b.max1 = a.get<float>((size_t)c.B * c.K1);
   b.idx0 = a.get<int>((size_t)c.B * c.K0);
@@ -228,6 +230,8 @@ int sg_forward(sfm_ctx* h, const SgCall& c, void* ws, size_t ws_bytes, bool dry,
   s.S = b.scores; s.B = c.B; s.N = c.K0; s.M = c.K1; s.alpha = h->sg.bin_score; s.iters = c.iters;
   s.u = b.u; s.v = b.v; s.part = b.part; s.counters = b.counters; s.R = b.R;
   s.fast = c.precision == 1;
+  s.fused_part = b.sk_fused;
+  s.kb = b.sk_kb;
   ProfScope ps(h, SFM_PROF_SINKHORN, st);
   SFM_TRY(sinkhorn_run(s, st));
   return sinkhorn_match(s, c.thr, b.max0, b.idx0, b.max1, b.idx1, c.m0, c.m1, c.ms0, c.ms1, st);

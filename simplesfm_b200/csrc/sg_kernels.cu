@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(256) sk_col_kernel(const float* __restrict__ S
     bi[q] = 0x7fffffff;
     int j = c0 + lane + 32 * q;
     vj[q] = (MODE == 1 && j < M) ? vin[(long long)b * (M + 1) + j] : 0.f;
+    if (MODE == 2) m[q] = -1.f;
   }
   if (MODE == 0) {
     // each warp folds 4 consecutive rows per step: 16 independent loads in flight per lane
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(256) sk_col_kernel(const float* __restrict__ S
       for (int q = 0; q < 4; q++) {
         int j = c0 + lane + 32 * q;
         if (j < M) {
-          float z = __fsub_rn(__fadd_rn(__fadd_rn(sr[32 * q], ui), vj[q]), norm);
+          float z = MODE == 2 ? sr[32 * q] * ui : __fsub_rn(__fadd_rn(__fadd_rn(sr[32 * q], ui), vj[q]), norm);
           if (z > m[q]) {
             m[q] = z;
             bi[q] = i;
@@ -293,6 +294,200 @@ __global__ void __launch_bounds__(256) sk_col_kernel(const float* __restrict__ S
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Scaling-form Sinkhorn (throughput mode).  The log-space iteration of the reference
+//   u_i = log_mu_i - LSE_j(Z_ij + v_j),  v_j = log_nu_j - LSE_i(Z_ij + u_i)        (superglue.py:142-148)
+// is algebraically the matrix-scaling iteration on K_ij = exp(S_ij - c_i) (c_i = row maximum, which keeps
+// every row representable), A_i = exp(u_i + c_i), B_j = exp(v_j):
+//   A_i = mu_i / (sum_j K_ij B_j + Kb_i B_M),   B_j = nu_j / (sum_i K_ij A_i + e^alpha A_N)
+// with the dustbin column Kb_i = exp(alpha - c_i) and dustbin row e^alpha handled analytically.
+// One exponential per element ONCE, then every iteration is two FMAs per element and the matrix is read
+// from HBM a single time per iteration (fused row + column sweep).  fp32 throughout: the result differs
+// from the log-space path only by rounding (<< the bf16 noise of the descriptors feeding it).
+constexpr int FUSED_RB = 64;
+
+// prologue: c_i = max_j S_ij ; S_ij <- exp(S_ij - c_i) in place ; kb_i = exp(alpha - c_i).  Warp per row.
+__global__ void __launch_bounds__(256) sks_prologue_kernel(float* __restrict__ S, int N, int M, float alpha,
+                                                           float* __restrict__ kb) {
+  const int b = blockIdx.y;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  float* sr = S + ((long long)b * N + row) * M;
+  float m = -INFINITY;
+  for (int j = lane; j < M; j += 32) m = fmaxf(m, sr[j]);
+  m = warp_max(m);
+  for (int j = lane; j < M; j += 32) sr[j] = __expf(sr[j] - m);
+  if (lane == 0) kb[(long long)b * N + row] = __expf(alpha - m);
+}
+
+// fused sweep: A for the rows of this block, then the block's column sums of K_ij A_i
+template <int G>
+__global__ void __launch_bounds__(256) sks_fused_kernel(const float* __restrict__ K, int N, int M, float ealpha,
+                                                        const float* __restrict__ kb, const float* __restrict__ Bv,
+                                                        float* __restrict__ Av, float* __restrict__ part, float mu,
+                                                        float mu_bin) {
+  constexpr int RS = 16 / G;
+  __shared__ float red[2][8][RS];
+  __shared__ float red_bin[8];
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* Kb_ = K + (long long)b * N * M;
+  const float* Bb = Bv + (long long)b * (M + 1);
+  float* Ab = Av + (long long)b * (N + 1);
+  const float* kbb = kb + (long long)b * N;
+  float bj[4 * G];
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    const int col = (g * 256 + tid) * 4;
+#pragma unroll
+    for (int e = 0; e < 4; e++) bj[4 * g + e] = col < M ? Bb[col + e] : 0.f;   // (M+1)-strided: scalar loads
+  }
+  const float bbin = Bb[M];
+  if (blk == 0) {   // dustbin row: A_N = mu_bin / (e^alpha (sum_j B_j + B_M))
+    float sacc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4 * G; c++) sacc += bj[c];
+    sacc = warp_sum(sacc);
+    if (lane == 0) red_bin[warp] = sacc;
+    __syncthreads();
+    if (tid == 0) {
+      float tot = bbin;
+#pragma unroll
+      for (int w = 0; w < 8; w++) tot += red_bin[w];
+      Ab[N] = mu_bin / (ealpha * tot);
+    }
+  }
+  float cs[4 * G];
+#pragma unroll
+  for (int c = 0; c < 4 * G; c++) cs[c] = 0.f;
+  const int row0 = blk * FUSED_RB;
+  int par = 0;
+  for (int step = 0; step < FUSED_RB / RS; step++, par ^= 1) {
+    const int i0 = row0 + step * RS;
+    if (i0 >= N) break;   // block-uniform
+    float x[RS][4 * G];
+#pragma unroll
+    for (int r = 0; r < RS; r++) {
+      const bool rok = i0 + r < N;
+      const float* sr = Kb_ + (long long)(i0 + r) * M;
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const int col = (g * 256 + tid) * 4;
+        float4 t = (rok && col < M) ? *reinterpret_cast<const float4*>(sr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[r][4 * g] = t.x; x[r][4 * g + 1] = t.y; x[r][4 * g + 2] = t.z; x[r][4 * g + 3] = t.w;
+      }
+    }
+    float rsum[RS];
+#pragma unroll
+    for (int r = 0; r < RS; r++) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4 * G; c++) sacc = fmaf(x[r][c], bj[c], sacc);
+      rsum[r] = warp_sum(sacc);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < RS; r++) red[par][warp][r] = rsum[r];
+    }
+    __syncthreads();
+    float ai[RS];
+#pragma unroll
+    for (int r = 0; r < RS; r++) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; w++) tot += red[par][w][r];
+      const bool rok = i0 + r < N;
+      const float kbr = rok ? kbb[i0 + r] : 1.f;
+      ai[r] = rok ? mu / fmaf(kbr, bbin, tot) : 0.f;
+    }
+    if (warp == 0 && lane < RS && i0 + lane < N) {
+      float val = ai[0];
+#pragma unroll
+      for (int r = 1; r < RS; r++) val = lane == r ? ai[r] : val;
+      Ab[i0 + lane] = val;
+    }
+#pragma unroll
+    for (int c = 0; c < 4 * G; c++)
+#pragma unroll
+      for (int r = 0; r < RS; r++) cs[c] = fmaf(x[r][c], ai[r], cs[c]);
+  }
+  float* pb = part + ((long long)b * gridDim.x + blk) * M;
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    const int col = (g * 256 + tid) * 4;
+    if (col < M) *reinterpret_cast<float4*>(pb + col) = make_float4(cs[4 * g], cs[4 * g + 1], cs[4 * g + 2], cs[4 * g + 3]);
+  }
+}
+
+// B_j = nu / (sum over row blocks + e^alpha A_N);  last block: B_M = nu_bin / (sum_i kb_i A_i + e^alpha A_N)
+__global__ void __launch_bounds__(256) sks_combine_kernel(const float* __restrict__ part, int nblk, int N, int M,
+                                                          float ealpha, const float* __restrict__ kb,
+                                                          const float* __restrict__ Av, float* __restrict__ Bv,
+                                                          float nu, float nu_bin) {
+  __shared__ float red[8];
+  const int b = blockIdx.y;
+  const float* Ab = Av + (long long)b * (N + 1);
+  float* Bb = Bv + (long long)b * (M + 1);
+  const float an = Ab[N];
+  if (blockIdx.x == gridDim.x - 1) {
+    const float* kbb = kb + (long long)b * N;
+    float sacc = 0.f;
+    for (int i = threadIdx.x; i < N; i += 256) sacc = fmaf(kbb[i], Ab[i], sacc);
+    sacc = warp_sum(sacc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = ealpha * an;
+#pragma unroll
+      for (int w = 0; w < 8; w++) tot += red[w];
+      Bb[M] = nu_bin / tot;
+    }
+    return;
+  }
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= M) return;
+  const float* p = part + (long long)b * nblk * M + j;
+  float tot = ealpha * an;
+  for (int k = 0; k < nblk; k++) tot += p[(long long)k * M];
+  Bb[j] = nu / tot;
+}
+
+// row argmax of K_ij B_j (== argmax of the log assignment); matching score = K A B (N + M)
+__global__ void __launch_bounds__(256) sks_row_argmax_kernel(const float* __restrict__ K, int N, int M,
+                                                             const float* __restrict__ Av,
+                                                             const float* __restrict__ Bv, float scale,
+                                                             float* __restrict__ max0, int* __restrict__ idx0) {
+  const int b = blockIdx.y;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* sr = K + ((long long)b * N + row) * M;
+  const float* Bb = Bv + (long long)b * (M + 1);
+  float best = -1.f;
+  int bi = 0x7fffffff;
+  for (int j = lane; j < M; j += 32) {
+    const float z = sr[j] * Bb[j];
+    if (z > best) {
+      best = z;
+      bi = j;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (b2 > best || (b2 == best && i2 < bi)) {
+      best = b2;
+      bi = i2;
+    }
+  }
+  if (lane == 0) {
+    max0[(long long)b * N + row] = best * Av[(long long)b * (N + 1) + row] * scale;   // probability, not log
+    idx0[(long long)b * N + row] = bi == 0x7fffffff ? 0 : bi;
+  }
+}
+
 // row argmax of ((S_ij + u_i) + v_j) - norm over j < M, first index on ties; one warp per row
 __global__ void __launch_bounds__(256) sk_row_argmax_kernel(const float* __restrict__ S, int N, int M,
                                                             const float* __restrict__ u, const float* __restrict__ v,
@@ -330,8 +525,9 @@ __global__ void __launch_bounds__(256) sk_row_argmax_kernel(const float* __restr
 }
 
 __global__ void mutual_kernel(const float* __restrict__ max0, const int* __restrict__ idx0,
-                              const int* __restrict__ idx1, int N, int M, float thr, long long* __restrict__ m0,
-                              long long* __restrict__ m1, float* __restrict__ ms0, float* __restrict__ ms1) {
+                              const int* __restrict__ idx1, int N, int M, float thr, int is_prob,
+                              long long* __restrict__ m0, long long* __restrict__ m1, float* __restrict__ ms0,
+                              float* __restrict__ ms1) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const float* mx = max0 + (long long)b * N;
@@ -340,7 +536,7 @@ __global__ void mutual_kernel(const float* __restrict__ max0, const int* __restr
   if (t < N) {
     int j = i0[t];
     bool mutual = (i1[j] == t);
-    float sc = mutual ? expf(mx[t]) : 0.f;
+    float sc = mutual ? (is_prob ? mx[t] : expf(mx[t])) : 0.f;
     bool valid = mutual && sc > thr;
     m0[(long long)b * N + t] = valid ? (long long)j : -1ll;
     ms0[(long long)b * N + t] = sc;
@@ -349,7 +545,7 @@ __global__ void mutual_kernel(const float* __restrict__ max0, const int* __restr
     int i = i1[t];
     bool mutual1 = (i0[i] == t);
     bool mutual0 = (i1[i0[i]] == i);
-    float sc0 = mutual0 ? expf(mx[i]) : 0.f;
+    float sc0 = mutual0 ? (is_prob ? mx[i] : expf(mx[i])) : 0.f;
     bool valid0 = mutual0 && sc0 > thr;
     m1[(long long)b * M + t] = (mutual1 && valid0) ? (long long)i : -1ll;
     ms1[(long long)b * M + t] = mutual1 ? sc0 : 0.f;
@@ -523,6 +719,10 @@ size_t sinkhorn_partial_floats(int B, int N, int M, int* R_out) {
   if (R_out) *R_out = R;
   return (size_t)B * R * (M + 1) * 2;
 }
+size_t sinkhorn_fused_floats(int B, int N, int M) { return (size_t)B * cdiv(N, FUSED_RB) * M; }
+bool sinkhorn_use_scaling(const SinkhornArgs& a) {
+  return a.fast && a.fused_part != nullptr && a.kb != nullptr && a.M % 4 == 0 && a.M <= 4096 && a.iters > 0;
+}
 size_t sinkhorn_counter_ints(int B, int M) { return (size_t)B * cdiv(M, 128); }
 
 int sinkhorn_run(const SinkhornArgs& a, cudaStream_t st) {
@@ -537,6 +737,28 @@ int sinkhorn_run(const SinkhornArgs& a, cudaStream_t st) {
   fill_kernel<<<cdiv(nv, 256), 256, 0, st>>>(a.v, nv, 0.f);
   fill_kernel<<<cdiv(nu, 256), 256, 0, st>>>(a.u, nu, 0.f);
   SFM_LAUNCH_CHECK_N(2);
+  if (sinkhorn_use_scaling(a)) {
+    const int nblk = cdiv(N, FUSED_RB);
+    const float ealpha = expf(a.alpha);
+    const float mu = 1.0f / ((float)N + (float)M), mu_bin = (float)M * mu, nu_bin = (float)N * mu;
+    float* K = const_cast<float*>(a.S);   // the score matrix is overwritten by K = exp(S - rowmax)
+    sks_prologue_kernel<<<dim3(cdiv(N, 8), B), 256, 0, st>>>(K, N, M, a.alpha, a.kb);
+    fill_kernel<<<cdiv(nv, 256), 256, 0, st>>>(a.v, nv, 1.f);   // B = exp(v) = 1
+    dim3 fgrid(nblk, B);
+    dim3 cg(cdiv(M, 256) + 1, B);
+    for (int it = 0; it < a.iters; it++) {
+      if (M <= 1024)
+        sks_fused_kernel<1><<<fgrid, 256, 0, st>>>(K, N, M, ealpha, a.kb, a.v, a.u, a.fused_part, mu, mu_bin);
+      else if (M <= 2048)
+        sks_fused_kernel<2><<<fgrid, 256, 0, st>>>(K, N, M, ealpha, a.kb, a.v, a.u, a.fused_part, mu, mu_bin);
+      else
+        sks_fused_kernel<4><<<fgrid, 256, 0, st>>>(K, N, M, ealpha, a.kb, a.v, a.u, a.fused_part, mu, mu_bin);
+      sks_combine_kernel<<<cg, 256, 0, st>>>(a.fused_part, nblk, N, M, ealpha, a.kb, a.u, a.v, mu, nu_bin);
+    }
+    count_launches(2 + 2 * a.iters);
+    SFM_CUDA(cudaGetLastError());
+    return SFM_OK;
+  }
   const int sub = sinkhorn_sub_batch(B, N, M);
   for (int b0 = 0; b0 < B; b0 += sub) {
     const int nb = (B - b0) < sub ? (B - b0) : sub;
@@ -582,9 +804,18 @@ int sinkhorn_match(const SinkhornArgs& a, float thr, float* max0, int* idx0, flo
   const int B = a.B, N = a.N, M = a.M;
   if (B == 0) return SFM_OK;
   const float norm = -logf((float)N + (float)M);
-  SFM_TRY(argmax_rows_cols(a, norm, max0, idx0, max1, idx1, st));
   dim3 mgrid(cdiv(N > M ? N : M, 256), B);
-  mutual_kernel<<<mgrid, 256, 0, st>>>(max0, idx0, idx1, N, M, thr, matches0, matches1, mscores0, mscores1);
+  if (sinkhorn_use_scaling(a)) {
+    // a.S now holds K, a.u = A, a.v = B: assignment probabilities are K A B (N + M)
+    sks_row_argmax_kernel<<<dim3(cdiv(N, 8), B), 256, 0, st>>>(a.S, N, M, a.u, a.v, (float)N + (float)M, max0, idx0);
+    sk_col_kernel<2, false><<<dim3(cdiv(M, 128), a.R, B), 256, 0, st>>>(a.S, N, M, a.alpha, a.u, a.v, nullptr, a.part,
+                                                                        a.counters, a.R, 0.f, 0.f, max1, idx1);
+    mutual_kernel<<<mgrid, 256, 0, st>>>(max0, idx0, idx1, N, M, thr, 1, matches0, matches1, mscores0, mscores1);
+    SFM_LAUNCH_CHECK_N(3);
+    return SFM_OK;
+  }
+  SFM_TRY(argmax_rows_cols(a, norm, max0, idx0, max1, idx1, st));
+  mutual_kernel<<<mgrid, 256, 0, st>>>(max0, idx0, idx1, N, M, thr, 0, matches0, matches1, mscores0, mscores1);
   SFM_LAUNCH_CHECK();
   return SFM_OK;
 }

@@ -28,11 +28,15 @@ struct SinkhornArgs {
   float* part;      // [B, R, M+1, 2] column partials
   int* counters;    // [B, colblocks] zero-initialised, self-resetting
   int R;            // row splits of the column pass
+  float* fused_part = nullptr;  // [B, ceil(N/64), M] column partial sums of the fused single-read sweep
+  float* kb = nullptr;          // [B, N] dustbin-column factors exp(alpha - rowmax) of the scaling form
   int sub_batch = 0;  // pairs per L2-resident sweep group (0 = auto)
   bool fast = false;  // ex2.approx exponentials (bf16 precision mode) instead of IEEE expf
 };
 size_t sinkhorn_partial_floats(int B, int N, int M, int* R_out);
 size_t sinkhorn_counter_ints(int B, int M);
+size_t sinkhorn_fused_floats(int B, int N, int M);
+bool sinkhorn_use_scaling(const SinkhornArgs& a);
 int sinkhorn_run(const SinkhornArgs& a, cudaStream_t st);
 // mutual nearest neighbour + threshold from S, u, v  (never materialises the (N+1)x(M+1) matrix)
 int sinkhorn_match(const SinkhornArgs& a, float match_threshold, float* max0, int* idx0, float* max1, int* idx1,
