@@ -158,6 +158,12 @@ SFM_API int sfm_tc_attention(sfm_handle_t h, const void* qkv, long long rows_tot
                              long long q_row0_0, long long k_row0_0, int Nq1, int Nk1, long long q_row0_1,
                              long long k_row0_1, void* out_bf16, void* stream);
 
+/* sfm_tc_conv3x3: 3x3 / pad 1 convolution + bias (+ ReLU) as a tcgen05 implicit GEMM (SuperPoint encoder and heads,
+ *   superpoint.py:84-99): in [n,H,W,Cin] bf16 NHWC, w [Cout, 9*Cin] bf16 ordered (ky,kx,ci), out [n,H,W,Cout] bf16;
+ *   Cin in {64,128}, Cout in {64,128,256}. */
+SFM_API int sfm_tc_conv3x3(sfm_handle_t h, const void* in_nhwc, const void* w, const float* bias, void* out_nhwc,
+                           int n, int H, int W, int Cin, int Cout, int relu, void* stream);
+
 /* Matcher.__super_glue_matcher tail (matcher.py:103-109): per pair (L,2) uint32 rows
  * [i, matches0[i]] for matches0[i] > -1, in ascending i.  tables (B,K0,2) u32, lengths (B) i32. */
 SFM_API int sfm_compact_matches(const int64_t* matches0, int B, int K0, uint32_t* tables, int* lengths, void* stream);

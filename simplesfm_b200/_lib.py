@@ -66,6 +66,8 @@ _SIGNATURES = {
     "sfm_tc_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_longlong,
                                    C.c_longlong, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p,
                                    C.c_void_p]),
+    "sfm_tc_conv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sfm_compact_matches": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sfm_simple_match_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "sfm_simple_match": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,

@@ -214,6 +214,7 @@ int sfm_load_superpoint(sfm_handle_t h, const float* packed, size_t n) {
     c.cin = cin; c.cout = cout; c.k = k;
     SFM_TRY(upload(h, wk, &c.w));
     SFM_TRY(upload(h, b, &c.b));
+    SFM_TRY(upload_bf16(h, wk, &c.w_h));
   }
   h->sp.loaded = true;
   return SFM_OK;
@@ -494,6 +495,15 @@ int sfm_tc_attention(sfm_handle_t h, const void* qkv, long long rows_total, int 
   a.Nq[0] = Nq0; a.Nk[0] = Nk0; a.q_row0[0] = q_row0_0; a.k_row0[0] = k_row0_0;
   a.Nq[1] = Nq1; a.Nk[1] = Nk1; a.q_row0[1] = q_row0_1; a.k_row0[1] = k_row0_1;
   return tc::tc_attention(a, (cudaStream_t)stream);
+}
+
+int sfm_tc_conv3x3(sfm_handle_t h, const void* in_nhwc, const void* w, const float* bias, void* out_nhwc, int n, int H,
+                   int W, int Cin, int Cout, int relu, void* stream) {
+  SFM_REQUIRE(h && in_nhwc && w && out_nhwc, "sfm_tc_conv3x3: NULL argument");
+  tc::TcConv p;
+  p.in = (const __nv_bfloat16*)in_nhwc; p.w = (const __nv_bfloat16*)w; p.bias = bias; p.out = (__nv_bfloat16*)out_nhwc;
+  p.n = n; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.relu = relu;
+  return tc::tc_conv3x3(p, h->sm_count, (cudaStream_t)stream);
 }
 
 // ---- SimpleMatcher ----------------------------------------------------------------------------

@@ -9,6 +9,7 @@ struct SpConv {
   int cin, cout, k;
   float* w;  // [cout][k*k*cin]  (ky, kx, ci) K-major  -- implicit-GEMM B operand
   float* b;  // [cout]
+  __nv_bfloat16* w_h;  // bf16 copy of w (tcgen05 path)
 };
 
 struct SgBn {

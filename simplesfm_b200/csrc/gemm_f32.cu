@@ -241,7 +241,8 @@ int launch_gemm(const GemmF32& p, cudaStream_t st) {
 
 // conv1a: one input channel.  Each thread: one pixel x 16 output channels (4 threads per pixel).
 __global__ void conv1a_kernel(const float* __restrict__ img, const float* __restrict__ w9,
-                              const float* __restrict__ bias, float* __restrict__ out, int n_img, int H, int W) {
+                              const float* __restrict__ bias, float* __restrict__ out,
+                              __nv_bfloat16* __restrict__ out_h, int n_img, int H, int W) {
   __shared__ float sw[64 * 9];
   __shared__ float sb[64];
   for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w9[i];
@@ -271,6 +272,17 @@ __global__ void conv1a_kernel(const float* __restrict__ img, const float* __rest
 #pragma unroll
     for (int t = 0; t < 9; t++) a = fmaf(v[t], sw[co * 9 + t], a);
     o[c] = fmaxf(a + sb[co], 0.f);
+  }
+  if (out_h != nullptr) {
+    uint4* dh = reinterpret_cast<uint4*>(out_h + pix * 64 + q * 16);
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(o[c * 8], o[c * 8 + 1]), h1 = __floats2bfloat162_rn(o[c * 8 + 2], o[c * 8 + 3]),
+                     h2 = __floats2bfloat162_rn(o[c * 8 + 4], o[c * 8 + 5]), h3 = __floats2bfloat162_rn(o[c * 8 + 6], o[c * 8 + 7]);
+      dh[c] = make_uint4(*reinterpret_cast<unsigned*>(&h0), *reinterpret_cast<unsigned*>(&h1),
+                         *reinterpret_cast<unsigned*>(&h2), *reinterpret_cast<unsigned*>(&h3));
+    }
+    return;
   }
   float4* dst = reinterpret_cast<float4*>(out + pix * 64 + q * 16);
 #pragma unroll
@@ -305,11 +317,11 @@ int gemm_f32_nt(const GemmF32& p, cudaStream_t st) { return launch_gemm<0>(p, st
 int gemm_f32_nn(const GemmF32& p, cudaStream_t st) { return launch_gemm<1>(p, st); }
 int conv3x3_f32(const GemmF32& p, cudaStream_t st) { return launch_gemm<2>(p, st); }
 
-int conv1a_f32(const float* img, const float* w9, const float* bias, float* out, int n_img, int H, int W,
-               cudaStream_t st) {
+int conv1a_f32(const float* img, const float* w9, const float* bias, float* out, __nv_bfloat16* out_h, int n_img,
+               int H, int W, cudaStream_t st) {
   long long total = (long long)n_img * H * W * 4;
   if (total == 0) return SFM_OK;
-  conv1a_kernel<<<cdiv(total, 256), 256, 0, st>>>(img, w9, bias, out, n_img, H, W);
+  conv1a_kernel<<<cdiv(total, 256), 256, 0, st>>>(img, w9, bias, out, out_h, n_img, H, W);
   SFM_LAUNCH_CHECK();
   return SFM_OK;
 }

@@ -37,8 +37,9 @@ int gemm_f32_nn(const GemmF32& p, cudaStream_t st);   // C = A * B
 int conv3x3_f32(const GemmF32& p, cudaStream_t st);   // implicit GEMM, NHWC
 
 // conv1a: single input channel, 3x3, pad 1, + bias + ReLU.  in [n,H,W], w [64][9], out NHWC [n,H,W,64]
-int conv1a_f32(const float* img, const float* w9, const float* bias, float* out, int n_img, int H, int W,
-               cudaStream_t st);
+// writes fp32 NHWC `out`, or bf16 NHWC `out_h` when that is non-null
+int conv1a_f32(const float* img, const float* w9, const float* bias, float* out, __nv_bfloat16* out_h, int n_img,
+               int H, int W, cudaStream_t st);
 // 2x2/2 max pool on NHWC fp32
 int maxpool2_nhwc_f32(const float* in, float* out, int n_img, int H, int W, int C, cudaStream_t st);
 

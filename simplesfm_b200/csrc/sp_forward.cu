@@ -3,22 +3,32 @@
 #include "context.cuh"
 #include "gemm_f32.cuh"
 #include "sp_post.cuh"
+#include "tc_path.cuh"
 
 namespace sfm {
 
 namespace {
 
 struct SpBuffers {
+  __nv_bfloat16 *A16, *B16, *feat16;   // bf16 path activations
   float *A, *Bf, *feat, *logits, *smap, *nms, *dmap, *cand_score;
   int *cand_pix, *block_tmp, *cand_counts;
   int cap;
 };
 
-void carve(Arena& a, int n, int H, int W, SpBuffers& b) {
+void carve(Arena& a, int n, int H, int W, int precision, SpBuffers& b) {
   const size_t full = (size_t)n * H * W;
   const size_t cells = (size_t)n * (H / 8) * (W / 8);
-  b.A = a.get<float>(full * 64);
-  b.Bf = a.get<float>(full * 64);
+  if (precision == 1) {
+    b.A16 = a.get<__nv_bfloat16>(full * 64);
+    b.B16 = a.get<__nv_bfloat16>(full * 64);
+    b.feat16 = a.get<__nv_bfloat16>(cells * 128);
+    b.A = b.Bf = nullptr;
+  } else {
+    b.A16 = b.B16 = b.feat16 = nullptr;
+    b.A = a.get<float>(full * 64);
+    b.Bf = a.get<float>(full * 64);
+  }
   b.feat = a.get<float>(cells * 128);
   b.logits = a.get<float>(cells * 65);
   b.smap = a.get<float>(full);
@@ -53,6 +63,54 @@ int conv(const SpConv& cv, const float* in, float* out, int n, int H, int W, boo
   return gemm_f32_nt(g, st);
 }
 
+// bf16 throughput path: the eight 3x3 encoder convs and the two head convs run as tcgen05 implicit GEMMs
+// (tc_conv.cu), the two 1x1 head convs on the tcgen05 GEMM with fp32 outputs, so that the exact
+// post-processing chain (softmax, NMS, selection, sampling) is shared with the fp32 path.
+int tconv(sfm_ctx* h, const SpConv& cv, const __nv_bfloat16* in, __nv_bfloat16* out, int n, int H, int W,
+          cudaStream_t st) {
+  tc::TcConv p;
+  p.in = in; p.w = cv.w_h; p.bias = cv.b; p.out = out;
+  p.n = n; p.H = H; p.W = W; p.Cin = cv.cin; p.Cout = cv.cout; p.relu = 1;
+  return tc::tc_conv3x3(p, h->sm_count, st);
+}
+
+int head1x1(sfm_ctx* h, const SpConv& cv, const __nv_bfloat16* in, float* out, long long rows, cudaStream_t st) {
+  tc::TcGemm g;
+  g.A = in; g.lda = cv.cin; g.a_rows = rows; g.W = cv.w_h; g.ldw = cv.cin; g.w_rows = cv.cout;
+  g.M = (int)rows; g.N = cv.cout; g.K = cv.cin; g.K1 = cv.cin; g.bias = cv.b;
+  g.out_f = out; g.out_f_ld = cv.cout;
+  return tc::tc_gemm(g, h->sm_count, st);
+}
+
+int detect_bf16(sfm_ctx* h, const float* images, int n, int H, int W, const unsigned char* mask, float thr,
+                int nms_radius, int border, int* cand_counts, const SpBuffers& b, cudaStream_t st) {
+  const SpConv* c = h->sp.conv;
+  SFM_TRY(conv1a_f32(images, c[0].w, c[0].b, nullptr, b.A16, n, H, W, st));
+  SFM_TRY(tconv(h, c[1], b.A16, b.B16, n, H, W, st));
+  SFM_TRY(tc::maxpool2_nhwc_bf16(b.B16, b.A16, n, H, W, 64, st));
+  SFM_TRY(tconv(h, c[2], b.A16, b.B16, n, H / 2, W / 2, st));
+  SFM_TRY(tconv(h, c[3], b.B16, b.A16, n, H / 2, W / 2, st));
+  SFM_TRY(tc::maxpool2_nhwc_bf16(b.A16, b.B16, n, H / 2, W / 2, 64, st));
+  SFM_TRY(tconv(h, c[4], b.B16, b.A16, n, H / 4, W / 4, st));
+  SFM_TRY(tconv(h, c[5], b.A16, b.B16, n, H / 4, W / 4, st));
+  SFM_TRY(tc::maxpool2_nhwc_bf16(b.B16, b.A16, n, H / 4, W / 4, 128, st));
+  const int hh = H / 8, ww = W / 8;
+  const long long cells = (long long)n * hh * ww;
+  SFM_TRY(tconv(h, c[6], b.A16, b.B16, n, hh, ww, st));
+  SFM_TRY(tconv(h, c[7], b.B16, b.feat16, n, hh, ww, st));
+  SFM_TRY(tconv(h, c[8], b.feat16, b.A16, n, hh, ww, st));                 // convPa
+  SFM_TRY(head1x1(h, c[9], b.A16, b.logits, cells, st));                    // convPb -> fp32 logits [cells, 65]
+  SFM_TRY(sp_softmax_shuffle(b.logits, 65, b.smap, n, hh, ww, st));
+  SFM_TRY(sp_nms(b.smap, b.nms, n, H, W, nms_radius, st));
+  SFM_TRY(tconv(h, c[10], b.feat16, b.A16, n, hh, ww, st));                // convDa
+  SFM_TRY(head1x1(h, c[11], b.A16, b.dmap, cells, st));                     // convDb -> fp32 descriptor map
+  SFM_TRY(sp_select(b.nms, mask, n, H, W, thr, border, b.block_tmp, b.cap, b.cand_pix, b.cand_score, b.cand_counts,
+                    st));
+  if (cand_counts)
+    SFM_CUDA(cudaMemcpyAsync(cand_counts, b.cand_counts, n * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return SFM_OK;
+}
+
 }  // namespace
 
 int sp_forward_detect(sfm_ctx* h, const float* images, int n, int H, int W, const unsigned char* mask, float thr,
@@ -60,10 +118,10 @@ int sp_forward_detect(sfm_ctx* h, const float* images, int n, int H, int W, cons
                       bool dry, size_t* need, cudaStream_t st) {
   SFM_REQUIRE(n >= 0 && H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0,
               "superpoint: H and W must be positive multiples of 8 (H=%d W=%d)", H, W);
-  SFM_REQUIRE(precision == 0, "superpoint: only the fp32 precision path is built (precision=%d)", precision);
+  SFM_REQUIRE(precision == 0 || precision == 1, "superpoint: unknown precision %d", precision);
   Arena a(dry ? nullptr : ws, dry ? 0 : ws_bytes);
   SpBuffers b;
-  carve(a, n, H, W, b);
+  carve(a, n, H, W, precision, b);
   if (need) *need = a.off;
   if (dry) return SFM_OK;
   if (a.overflow) {
@@ -73,8 +131,9 @@ int sp_forward_detect(sfm_ctx* h, const float* images, int n, int H, int W, cons
   SFM_REQUIRE(h != nullptr && h->sp.loaded, "superpoint: weights not loaded (call sfm_load_superpoint)");
   if (n == 0) return SFM_OK;
   const SpConv* c = h->sp.conv;
+  if (precision == 1) return detect_bf16(h, images, n, H, W, mask, thr, nms_radius, border, cand_counts, b, st);
   // encoder (superpoint.py:112-122)
-  SFM_TRY(conv1a_f32(images, c[0].w, c[0].b, b.A, n, H, W, st));
+  SFM_TRY(conv1a_f32(images, c[0].w, c[0].b, b.A, nullptr, n, H, W, st));
   SFM_TRY(conv(c[1], b.A, b.Bf, n, H, W, true, st));
   SFM_TRY(maxpool2_nhwc_f32(b.Bf, b.A, n, H, W, 64, st));
   SFM_TRY(conv(c[2], b.A, b.Bf, n, H / 2, W / 2, true, st));
@@ -106,12 +165,12 @@ int sp_forward_describe(sfm_ctx* h, int n, int H, int W, int max_kp, int align_c
                         float* kpts_xy, float* scores, float* desc, int* counts, void* ws, size_t ws_bytes,
                         cudaStream_t st) {
   (void)h;
-  SFM_REQUIRE(precision == 0, "superpoint: only the fp32 precision path is built (precision=%d)", precision);
+  SFM_REQUIRE(precision == 0 || precision == 1, "superpoint: unknown precision %d", precision);
   SFM_REQUIRE(max_kp == -1 || max_kp > 0, "\"max_keypoints\" must be positive or \"-1\"");
   SFM_REQUIRE(kp_cap >= 0, "superpoint: kp_cap < 0");
   Arena a(ws, ws_bytes);
   SpBuffers b;
-  carve(a, n, H, W, b);
+  carve(a, n, H, W, precision, b);
   if (a.overflow) {
     set_error("superpoint: workspace too small (%zu bytes given, %zu needed)", ws_bytes, a.off);
     return SFM_ERR_WORKSPACE;
@@ -123,10 +182,9 @@ int sp_forward_describe(sfm_ctx* h, int n, int H, int W, int max_kp, int align_c
 }
 
 int sp_tap(int n, int H, int W, int precision, int which, void* ws, size_t ws_bytes, float** out, size_t* cnt) {
-  (void)precision;
   Arena a(ws, ws_bytes);
   SpBuffers b;
-  carve(a, n, H, W, b);
+  carve(a, n, H, W, precision, b);
   if (a.overflow) {
     set_error("superpoint tap: workspace too small");
     return SFM_ERR_WORKSPACE;

@@ -63,6 +63,17 @@ struct TcAttn {
 };
 int tc_attention(const TcAttn& p, cudaStream_t st);
 
+// 3x3 / pad 1 convolution, NHWC bf16, implicit GEMM on tcgen05 with 4-D TMA im2col (tc_conv.cu)
+struct TcConv {
+  const __nv_bfloat16* in = nullptr;  // [n, H, W, Cin]
+  const __nv_bfloat16* w = nullptr;   // [Cout, 9 * Cin]  (tap-major, channel-minor)
+  const float* bias = nullptr;
+  __nv_bfloat16* out = nullptr;       // [n, H, W, Cout]
+  int n = 0, H = 0, W = 0, Cin = 0, Cout = 0, relu = 1;
+};
+int tc_conv3x3(const TcConv& p, int num_sms, cudaStream_t st);
+int maxpool2_nhwc_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int n, int H, int W, int C, cudaStream_t st);
+
 // elementwise / reduction helpers of the bf16 path
 int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);
 

@@ -76,7 +76,8 @@ class Matcher(object):
                  precision: str = 'fp32',
                  device: str = 'cuda',
                  shard_pairs: bool = True,
-                 fuse_chunks: int = 8):
+                 fuse_chunks: int = 8,
+                 superpoint_precision: str = 'fp32'):
 
         self.matcher_type = matcher_type
         self.device = torch.device(device)
@@ -89,7 +90,7 @@ class Matcher(object):
                                                 nms_radius=nms_radius,
                                                 keypoint_threshold=keypoint_threshold,
                                                 max_keypoints=max_keypoints,
-                                                device=device)
+                                                device=device, precision=superpoint_precision)
         self.super_point_extractor.cuda()
 
         if self.matcher_type == 'simple':

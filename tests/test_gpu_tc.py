@@ -147,3 +147,50 @@ def test_fused_chunks_equal_separate_chunks(sg_weights, dev):
     assert len(tabs[1]) == 21
     for k in tabs[1]:
         assert np.array_equal(tabs[1][k], tabs[4][k]), k
+
+
+@pytest.mark.parametrize("n,H,W,Cin,Cout", [(1, 16, 32, 64, 64), (2, 60, 80, 128, 256), (1, 120, 160, 64, 128),
+                                             (1, 24, 40, 128, 128), (1, 480, 640, 64, 64)])
+def test_tc_conv3x3(handle, dev, n, H, W, Cin, Cout):
+    """tcgen05 implicit-GEMM convolution (4-D TMA im2col, zero-fill padding) vs torch conv2d in fp32 on the
+    same bf16-rounded operands; H not a multiple of 8 / W not a multiple of 16 exercise partial tiles."""
+    from simplesfm_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(H * W + Cin)
+    x = torch.randn(n, Cin, H, W, generator=g).to(dev).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).to(dev).bfloat16()
+    bias = torch.randn(Cout, generator=g).to(dev)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    w_k = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()       # (ky, kx, ci)
+    out = torch.zeros(n, H, W, Cout, dtype=torch.bfloat16, device=dev)
+    _lib.check(_lib.lib().sfm_tc_conv3x3(handle.h, x_nhwc.data_ptr(), w_k.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                         n, H, W, Cin, Cout, 1, _stream()))
+    ref = torch.relu(torch.nn.functional.conv2d(x.float(), w.float(), bias, padding=1)).permute(0, 2, 3, 1)
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+def test_superpoint_bf16_vs_fp32(sp_weights, dev):
+    """SuperPoint with tcgen05 convolutions (bf16) against the exact fp32 path: dense maps within bf16
+    noise, and the detected keypoint sets overlap (stated-precision mode; keypoints are not bit-exact)."""
+    from simplesfm_b200 import synthetic
+    from simplesfm_b200.models.superpoint import SuperPoint
+    img = synthetic.textured_image(1).to(dev)
+    m32 = SuperPoint(sp_weights, max_keypoints=1024, device=dev, precision="fp32")
+    m16 = SuperPoint(sp_weights, max_keypoints=1024, device=dev, precision="bf16")
+    c32, ws32 = m32.detect(img[:, 0].contiguous())
+    l32 = m32.tap(1, 480, 640, 1, ws32).clone()
+    s32 = m32.tap(1, 480, 640, 2, ws32).clone()
+    c16, ws16 = m16.detect(img[:, 0].contiguous())
+    l16 = m16.tap(1, 480, 640, 1, ws16).clone()
+    s16 = m16.tap(1, 480, 640, 2, ws16).clone()
+    rel = float((l16 - l32).pow(2).mean().sqrt() / l32.pow(2).mean().sqrt())
+    print(f"SuperPoint bf16 logits rms rel err {rel:.4f}; score map max abs err {float((s16 - s32).abs().max()):.4f}")
+    assert rel < 0.03
+    o32, o16 = m32({"image": img}), m16({"image": img})
+    k32 = {tuple(r) for r in o32["keypoints"].cpu().numpy().tolist()}
+    k16 = {tuple(r) for r in o16["keypoints"].cpu().numpy().tolist()}
+    overlap = len(k32 & k16) / max(len(k32), 1)
+    print(f"SuperPoint bf16 keypoint overlap with fp32 (top-1024): {overlap:.3f}")
+    assert overlap > 0.85
+    assert o16["descriptors"].shape == (256, 1024)
+    close_norm = o16["descriptors"].norm(dim=0)
+    assert float((close_norm - 1).abs().max()) < 1e-3
