@@ -25,7 +25,7 @@ constexpr int ATT_THREADS = 320;
 struct AttBars {
   uint64_t q_full;
   uint64_t kv_full[KV_STAGES], kv_empty[KV_STAGES];
-  uint64_t s_full[2], p_full[2], o_full[2], o_free[2];
+  uint64_t s_full[2], s_free[2], p_full[2], o_full[2];
   uint32_t tmem_base;
 };
 
@@ -66,7 +66,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
       mbar_init(&bars->s_full[t], 1);
       mbar_init(&bars->p_full[t], 4);
       mbar_init(&bars->o_full[t], 1);
-      mbar_init(&bars->o_free[t], 4);
+      mbar_init(&bars->s_free[t], 4);
     }
     fence_barrier_init();
   }
@@ -119,17 +119,21 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
       issue_s(1, 0);
       for (int j = 0; j < n_kv; j++) {
         const int s = j % KV_STAGES;
-        for (int t = 0; t < 2; t++) {
-          mbar_wait(&bars->p_full[t], j & 1);  // P_t(j) written, S_t region drained
-          tc_fence_after();
-          if (j + 1 < n_kv) {
-            const int s1 = (j + 1) % KV_STAGES;
-            if (t == 0) {
-              mbar_wait(&bars->kv_full[s1], ((j + 1) / KV_STAGES) & 1);
-              tc_fence_after();
-            }
+        // (1) as soon as a warpgroup has pulled S_t(j) into registers its TMEM region is free again: issue
+        //     S_t(j+1) right away so that it is ready when the group finishes the exponentials of tile j
+        if (j + 1 < n_kv) {
+          const int s1 = (j + 1) % KV_STAGES;
+          mbar_wait(&bars->kv_full[s1], ((j + 1) / KV_STAGES) & 1);
+          for (int t = 0; t < 2; t++) {
+            mbar_wait(&bars->s_free[t], j & 1);
+            tc_fence_after();
             issue_s(t, s1);
           }
+        }
+        // (2) P_t(j) written (much later): accumulate O_t += P_t V_j
+        for (int t = 0; t < 2; t++) {
+          mbar_wait(&bars->p_full[t], j & 1);
+          tc_fence_after();
           const uint64_t vd = s == 0 ? v_desc[0] : (s == 1 ? v_desc[1] : v_desc[2]);
 #pragma unroll
           for (int k = 0; k < 8; k++)  // 16 keys per step: 16 V rows = 2048 bytes, P advances 8 columns
@@ -159,6 +163,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
       for (int ch = 0; ch < 4; ch++)
         tmem_ld_32x32(lane_addr + COL_S + t * 128 + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[ch * 32]));
       tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->s_free[t]);   // S_t is in registers: the tensor pipe may overwrite it
       if (valid < 128) {
 #pragma unroll
         for (int i = 0; i < 128; i++)
