@@ -143,6 +143,13 @@ SFM_API int sfm_sinkhorn_match(const float* scores, int B, int N, int M, float a
                        int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same contract in the throughput formulation (matrix-scaling Sinkhorn, see csrc/sg_kernels.cu): one exp per
+ * element once, then two FMAs per element per iteration and a single HBM read of the matrix per iteration.
+ * `scores` is OVERWRITTEN (it becomes exp(S - rowmax)).  Requires M % 4 == 0, M <= 4096, iters > 0. */
+SFM_API int sfm_sinkhorn_match_scaled(float* scores, int B, int N, int M, float alpha, int iters, float match_threshold,
+                                      int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
+                                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- kernel-level hooks of the bf16 tcgen05 path (tests/, bench) ---------------------------------
  * sfm_tc_gemm: out[M,N] = alpha * [A | A2][M,K] * W[N,K]^T + bias (bf16 operands, K in {256,512},
  *   K1 = columns taken from A); optional ReLU; writes bf16 and/or fp32 (accumulate: out_f32 += result,

@@ -407,7 +407,7 @@ int sfm_superglue_tap(int B, int K0, int K1, int precision, int chunk_groups, in
 // ---- optimal transport ------------------------------------------------------------------------
 namespace {
 struct OtBuffers {
-  float *u, *v, *part, *max0, *max1;
+  float *u, *v, *part, *max0, *max1, *fused, *kb;
   int *counters, *idx0, *idx1;
   int R;
 };
@@ -420,9 +420,11 @@ void ot_carve(Arena& a, int B, int N, int M, OtBuffers& b) {
   b.max1 = a.get<float>((size_t)B * M);
   b.idx0 = a.get<int>((size_t)B * N);
   b.idx1 = a.get<int>((size_t)B * M);
+  b.fused = a.get<float>(sinkhorn_fused_floats(B, N, M));
+  b.kb = a.get<float>((size_t)B * N);
 }
 int ot_prepare(const float* scores, int B, int N, int M, float alpha, int iters, void* ws, size_t ws_bytes,
-               OtBuffers& b, SinkhornArgs& s, cudaStream_t st) {
+               OtBuffers& b, SinkhornArgs& s, cudaStream_t st, bool scaled = false) {
   SFM_REQUIRE(scores && B >= 0 && N > 0 && M > 0 && iters >= 0, "sinkhorn: bad arguments (B=%d N=%d M=%d iters=%d)", B, N,
               M, iters);
   Arena a(ws, ws_bytes);
@@ -434,6 +436,11 @@ int ot_prepare(const float* scores, int B, int N, int M, float alpha, int iters,
   SFM_CUDA(cudaMemsetAsync(b.counters, 0, sinkhorn_counter_ints(B, M) * sizeof(int), st));
   s.S = scores; s.B = B; s.N = N; s.M = M; s.alpha = alpha; s.iters = iters;
   s.u = b.u; s.v = b.v; s.part = b.part; s.counters = b.counters; s.R = b.R;
+  if (scaled) {
+    s.fast = true;
+    s.fused_part = b.fused;
+    s.kb = b.kb;
+  }
   return sinkhorn_run(s, st);
 }
 }  // namespace
@@ -461,6 +468,18 @@ int sfm_sinkhorn_match(const float* scores, int B, int N, int M, float alpha, in
   OtBuffers b;
   SinkhornArgs s;
   SFM_TRY(ot_prepare(scores, B, N, M, alpha, iters, ws, ws_bytes, b, s, (cudaStream_t)stream));
+  return sinkhorn_match(s, match_threshold, b.max0, b.idx0, b.max1, b.idx1, (long long*)matches0, (long long*)matches1,
+                        mscores0, mscores1, (cudaStream_t)stream);
+}
+
+int sfm_sinkhorn_match_scaled(float* scores, int B, int N, int M, float alpha, int iters, float match_threshold,
+                              int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1, void* ws,
+                              size_t ws_bytes, void* stream) {
+  SFM_REQUIRE(matches0 && matches1 && mscores0 && mscores1, "sfm_sinkhorn_match_scaled: NULL output");
+  SFM_REQUIRE(M % 4 == 0 && M <= 4096 && iters > 0, "sfm_sinkhorn_match_scaled: needs M %% 4 == 0, M <= 4096, iters > 0");
+  OtBuffers b;
+  SinkhornArgs s;
+  SFM_TRY(ot_prepare(scores, B, N, M, alpha, iters, ws, ws_bytes, b, s, (cudaStream_t)stream, true));
   return sinkhorn_match(s, match_threshold, b.max0, b.idx0, b.max1, b.idx1, (long long*)matches0, (long long*)matches1,
                         mscores0, mscores1, (cudaStream_t)stream);
 }

@@ -1,0 +1,43 @@
+"""BASELINE config 5: log_optimal_transport + mutual matching microbench (N = M = 4096, 100 iterations by default).
+Reports pairs/s for the exact log-space path and the scaling-form throughput path, achieved HBM GB/s
+(algorithmic bytes: matrix reads per iteration x 4 B) and their match agreement."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from simplesfm_b200 import _lib
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+B = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+dev = torch.device("cuda:0")
+L = _lib.lib()
+h = _lib.Handle(dev)
+g = torch.Generator(device="cpu").manual_seed(0)
+S = (torch.randn(B, N, N, generator=g) * 2.0).to(dev)
+idx = torch.arange(N // 2)
+for b in range(B):
+    S[b, idx, torch.randperm(N, generator=g)[:N // 2].to(dev)] += 20.0
+ws = torch.empty(L.sfm_sinkhorn_workspace_bytes(B, N, N), dtype=torch.uint8, device=dev)
+out = lambda: (torch.empty(B, N, dtype=torch.int64, device=dev), torch.empty(B, N, dtype=torch.int64, device=dev),
+               torch.empty(B, N, device=dev), torch.empty(B, N, device=dev))
+st = torch.cuda.current_stream().cuda_stream
+res = {}
+for name in ("exact_logspace", "scaling_form"):
+    m0, m1, s0, s1 = out()
+    def run(Sx):
+        fn = L.sfm_sinkhorn_match if name == "exact_logspace" else L.sfm_sinkhorn_match_scaled
+        _lib.check(fn(Sx.data_ptr(), B, N, N, 1.0, iters, 0.2, m0.data_ptr(), m1.data_ptr(), s0.data_ptr(), s1.data_ptr(),
+                      ws.data_ptr(), ws.numel(), st))
+    run(S.clone())
+    torch.cuda.synchronize()
+    Sx = S.clone()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); run(Sx); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    reads = (2 if name == "exact_logspace" else 1) * iters + 3
+    res[name] = {"ms": ms, "pairs_per_s": B / ms * 1e3, "GBps_algorithmic": reads * B * N * N * 4 / ms / 1e6,
+                 "matches": int((m0 > -1).sum()), "m0": m0.clone()}
+a, b = res["exact_logspace"].pop("m0"), res["scaling_form"].pop("m0")
+both = (a > -1) | (b > -1)
+res["agreement"] = float(((a == b) & both).sum()) / max(int(both.sum()), 1)
+res["config"] = {"N": N, "M": N, "iters": iters, "batch": B}
+print(json.dumps(res))
