@@ -327,3 +327,63 @@ def test_matcher_images_e2e_golden(sp_weights, sg_weights_outdoor, dev):
         got = {(tuple(kps[a - 1][i]), tuple(kps[b - 1][j])) for i, j in tab.tolist()}
         want = {(tuple(g[f"kpts_{a - 1}"][i]), tuple(g[f"kpts_{b - 1}"][j])) for i, j in ref.tolist()}
         assert got == want, (a, b, len(got ^ want))
+
+
+def test_config1_pair_480x640_1024kp_vs_oracle(sp_weights, sg_weights, dev):
+    """BASELINE config 1: SuperPoint + SuperGlue (indoor layout, 100 Sinkhorn iterations, thr 0.2) on one
+    640x480 image pair with max_keypoints = 1024, fp32 path against the CPU oracle end to end."""
+    from simplesfm_b200 import synthetic
+    from simplesfm_b200.models.superglue import SuperGlue
+    from simplesfm_b200.models.superpoint import SuperPoint
+    imgs = [synthetic.textured_image(11, shift=(0, 0)), synthetic.textured_image(11, shift=(5, -7))]
+    sp = SuperPoint(sp_weights, max_keypoints=1024, device=dev)
+    sgm = SuperGlue(sg_weights, sinkhorn_iterations=100, match_threshold=0.2, device=dev)
+    feats, ofeats = [], []
+    for im in imgs:
+        r = sp({"image": im.to(dev)})
+        o = O.superpoint_forward(sp_weights, im, None, 4, 0.005, 1024, 4)
+        assert {tuple(x) for x in r["keypoints"].cpu().numpy().tolist()} == \
+               {tuple(x) for x in o["keypoints"].numpy().tolist()}
+        feats.append(r)
+        ofeats.append(o)
+    # feed the ORACLE's features to both matchers so that the comparison isolates SuperGlue
+    data = {"descriptors0": ofeats[0]["descriptors"][None], "descriptors1": ofeats[1]["descriptors"][None],
+            "keypoints0": ofeats[0]["keypoints"][None], "keypoints1": ofeats[1]["keypoints"][None],
+            "scores0": ofeats[0]["scores"][None], "scores1": ofeats[1]["scores"][None],
+            "image0": imgs[0], "image1": imgs[1]}
+    ref = O.superglue_forward(sg_weights, data, 100, 0.2, "train")
+    out = sgm({k: v.to(dev) for k, v in data.items()})
+    a, b = out["matches0"].cpu().numpy(), ref["matches0"].numpy()
+    assert (b > -1).sum() > 20
+    assert np.array_equal(a, b)
+    close(out["matching_scores0"], ref["matching_scores0"], 1e-3, 1e-5)
+    # and the GPU's own descriptors agree with the oracle's for the same keypoints
+    for r, o in zip(feats, ofeats):
+        kp, okp = r["keypoints"].cpu().numpy(), o["keypoints"].numpy()
+        idx = {tuple(x): i for i, x in enumerate(kp.tolist())}
+        perm = [idx[tuple(x)] for x in okp.tolist()]
+        close(r["descriptors"].cpu().numpy()[:, perm], o["descriptors"].numpy(), 1e-4, 1e-5)
+
+
+def test_matcher_edge_cases(sp_weights, sg_weights, dev):
+    """No pairs, a frame without keypoints (reference early-out: empty table), ragged chunk at the end."""
+    from simplesfm_b200 import synthetic
+    from simplesfm_b200.matchers import Matcher
+    from simplesfm_b200.matchers.matcher import Frame
+    fr = synthetic.feature_scene(4, 64, seed=2)
+    img = torch.zeros(1, 480, 640, device=dev)
+    frames = [Frame(d.to(dev), k.to(dev), s.to(dev), img) for d, k, s in fr]
+    frames[2] = Frame(torch.zeros(256, 0, device=dev), torch.zeros(0, 2, device=dev), torch.zeros(0, device=dev), img)
+    m = Matcher(sp_weights, 4, 0.005, matcher_type="super_glue", super_glue_weights_path=sg_weights,
+                match_threshold=0.2, sinkhorn_iterations=5, super_glue_batch=1, device=dev)
+    names = {i + 1: str(i) for i in range(4)}
+    _, table, _ = m.match_frames(frames, names, lambda p: True)
+    assert len(table) == 6
+    for (a, b), t_ in table.items():
+        assert t_.dtype == np.uint32 and t_.shape[1] == 2
+        if 3 in (int(a), int(b)):
+            assert len(t_) == 0
+    _, table, _ = m.match_frames(frames, names, lambda p: False)
+    assert table == {}
+    _, table, _ = m.match_frames(frames[:1], {1: "0"}, None)
+    assert table == {}

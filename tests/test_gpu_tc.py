@@ -194,3 +194,27 @@ def test_superpoint_bf16_vs_fp32(sp_weights, dev):
     assert o16["descriptors"].shape == (256, 1024)
     close_norm = o16["descriptors"].norm(dim=0)
     assert float((close_norm - 1).abs().max()) < 1e-3
+
+
+def test_superglue_4096kp_full_size(sg_weights, dev):
+    """BASELINE config 4 keypoint count (4096) on one pair: the bf16 path against the fp32 path, plus the
+    size-independent structure of the outputs (mutual consistency of matches0 / matches1)."""
+    from simplesfm_b200 import synthetic
+    from simplesfm_b200.models.superglue import SuperGlue
+    K = 4096
+    fr = synthetic.feature_scene(2, K, seed=12)
+    data = {"descriptors0": fr[0][0][None].to(dev), "descriptors1": fr[1][0][None].to(dev),
+            "keypoints0": fr[0][1][None].to(dev), "keypoints1": fr[1][1][None].to(dev),
+            "scores0": fr[0][2][None].to(dev), "scores1": fr[1][2][None].to(dev),
+            "image0": torch.zeros(1, 1, 480, 640), "image1": torch.zeros(1, 1, 480, 640)}
+    ref = SuperGlue(sg_weights, sinkhorn_iterations=20, match_threshold=0.4, precision="fp32", device=dev)(data)
+    out = SuperGlue(sg_weights, sinkhorn_iterations=20, match_threshold=0.4, precision="bf16", device=dev)(data)
+    for res in (ref, out):
+        m0, m1 = res["matches0"][0].cpu(), res["matches1"][0].cpu()
+        v = m0 > -1
+        assert torch.equal(m1[m0[v]], torch.nonzero(v)[:, 0])
+        assert (res["matching_scores0"][0].cpu()[v] > 0.4).all()
+    agree = _agreement(out["matches0"], ref["matches0"])
+    n_ref = int((ref["matches0"] > -1).sum())
+    print(f"4096 kp: bf16 vs fp32 agreement {agree:.4f} over {n_ref} matches")
+    assert n_ref > 500 and agree >= 0.99
