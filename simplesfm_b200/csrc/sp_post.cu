@@ -38,22 +38,28 @@ __global__ void softmax_shuffle_kernel(const float* __restrict__ logits, int ldl
 // simple_nms: 32x32 output tile, halo 5*r, separable (2r+1)-max in shared memory.
 constexpr int NMS_TILE = 32;
 
+// Separable (2r+1)-max restricted to where it is needed: `in` is meaningful on [mg, T-mg)^2, the result on
+// [mg+r, T-mg-r)^2 (every pool of the chain shrinks the valid region by r, so later pools touch fewer pixels).
 __device__ __forceinline__ void pool_sep(const float* __restrict__ in, float* __restrict__ tmp,
-                                         float* __restrict__ out, int T, int r) {
-  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
-    int y = i / T, x = i - y * T;
-    int lo = max(x - r, 0), hi = min(x + r, T - 1);
-    float m = -INFINITY;
-    for (int k = lo; k <= hi; k++) m = fmaxf(m, in[y * T + k]);
-    tmp[i] = m;
+                                         float* __restrict__ out, int T, int r, int mg) {
+  const int lo = mg, hi = T - mg;            // input extent
+  const int olo = mg + r, ohi = T - mg - r;  // output extent
+  const int wout = ohi - olo, hin = hi - lo;
+  if (wout <= 0) return;
+  for (int i = threadIdx.x; i < hin * wout; i += blockDim.x) {
+    const int y = lo + i / wout, x = olo + i % wout;
+    const float* p = in + y * T + x - r;
+    float m = p[0];
+    for (int k = 1; k <= 2 * r; k++) m = fmaxf(m, p[k]);
+    tmp[y * T + x] = m;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
-    int y = i / T, x = i - y * T;
-    int lo = max(y - r, 0), hi = min(y + r, T - 1);
-    float m = -INFINITY;
-    for (int k = lo; k <= hi; k++) m = fmaxf(m, tmp[k * T + x]);
-    out[i] = m;
+  for (int i = threadIdx.x; i < wout * wout; i += blockDim.x) {
+    const int y = olo + i / wout, x = olo + i % wout;
+    const float* p = tmp + (y - r) * T + x;
+    float m = p[0];
+    for (int k = 1; k <= 2 * r; k++) m = fmaxf(m, p[k * T]);
+    out[y * T + x] = m;
   }
   __syncthreads();
 }
@@ -77,32 +83,39 @@ __global__ void nms_kernel(const float* __restrict__ scores, float* __restrict__
     s[i] = in ? src[(long long)y * W + x] : -INFINITY;
   }
   __syncthreads();
-  pool_sep(s, tmp, pl, T, r);
+  pool_sep(s, tmp, pl, T, r, 0);           // valid on margin r
   for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
-    int y = y0 + i / T, x = x0 + i % T;
+    int ty = i / T, tx = i % T;
+    int y = y0 + ty, x = x0 + tx;
     bool in = y >= 0 && y < H && x >= 0 && x < W;
-    mx[i] = (in && s[i] == pl[i]) ? 1 : 0;
+    bool val = ty >= r && ty < T - r && tx >= r && tx < T - r;   // pl is only defined there
+    mx[i] = (in && val && s[i] == pl[i]) ? 1 : 0;
   }
   __syncthreads();
   for (int round = 0; round < 2; round++) {
     for (int i = threadIdx.x; i < T * T; i += blockDim.x) a[i] = mx[i] ? 1.f : 0.f;
     __syncthreads();
-    pool_sep(a, tmp, pl, T, r);           // pl > 0  <=> suppressed neighbourhood
+    const int m1 = r * (1 + 2 * round);
+    pool_sep(a, tmp, pl, T, r, m1);       // pl > 0  <=> suppressed neighbourhood (valid on margin m1 + r)
     for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
       int y = y0 + i / T, x = x0 + i % T;
       bool in = y >= 0 && y < H && x >= 0 && x < W;
-      bool supp = pl[i] > 0.f;
+      int ty = i / T, tx = i % T;
+      bool val = ty >= m1 + r && ty < T - m1 - r && tx >= m1 + r && tx < T - m1 - r;
+      bool supp = val && pl[i] > 0.f;
       a[i] = in ? (supp ? 0.f : s[i]) : -INFINITY;
       // stash supp in bit 1 of mx
       mx[i] = (mx[i] & 1) | (supp ? 2 : 0);
     }
     __syncthreads();
-    pool_sep(a, tmp, pl, T, r);
+    pool_sep(a, tmp, pl, T, r, m1 + r);   // valid on margin m1 + 2r
     for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
-      int y = y0 + i / T, x = x0 + i % T;
+      int ty = i / T, tx = i % T;
+      int y = y0 + ty, x = x0 + tx;
       bool in = y >= 0 && y < H && x >= 0 && x < W;
+      bool val = ty >= m1 + 2 * r && ty < T - m1 - 2 * r && tx >= m1 + 2 * r && tx < T - m1 - 2 * r;
       bool supp = mx[i] & 2;
-      bool nm = in && (a[i] == pl[i]) && !supp;
+      bool nm = in && val && (a[i] == pl[i]) && !supp;
       mx[i] = ((mx[i] & 1) || nm) ? 1 : 0;
     }
     __syncthreads();
@@ -366,7 +379,7 @@ int sp_nms(const float* scores, float* out, int n_img, int H, int W, int radius,
     configured = smem;
   }
   dim3 grid(cdiv(W, NMS_TILE), cdiv(H, NMS_TILE), n_img);
-  nms_kernel<<<grid, 256, smem, st>>>(scores, out, H, W, radius);
+  nms_kernel<<<grid, 512, smem, st>>>(scores, out, H, W, radius);
   SFM_LAUNCH_CHECK();
   return SFM_OK;
 }

@@ -12,6 +12,7 @@
 // than 2^8 (lazy rescale: probabilities stay <= 256, exact after the final division by the sum).
 #include "tc_common.cuh"
 #include "tc_path.cuh"
+#include <stdlib.h>
 
 namespace sfm {
 namespace tc {
@@ -20,7 +21,7 @@ namespace {
 
 constexpr int KV_STAGES = 3;
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, 128-byte swizzled rows
-constexpr int ATT_THREADS = 320;
+template <int NT> struct AttCfg { static constexpr int THREADS = 64 + NT * 128; };
 
 struct AttBars {
   uint64_t q_full;
@@ -29,12 +30,13 @@ struct AttBars {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int NT>
+__global__ void __launch_bounds__(64 + NT * 128, NT == 1 ? 2 : 1)
 tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units0, int qt0, int qt1) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                         // 2 tiles
-  uint8_t* sK = smem + 2 * TILE_BYTES;        // KV_STAGES tiles
+  uint8_t* sQ = smem;                         // NT tiles
+  uint8_t* sK = smem + NT * TILE_BYTES;       // KV_STAGES tiles
   uint8_t* sV = sK + KV_STAGES * TILE_BYTES;  // KV_STAGES tiles
   AttBars* bars = reinterpret_cast<AttBars*>(sV + KV_STAGES * TILE_BYTES);
 
@@ -51,7 +53,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
   const int qblk = (u >> 2) % qts;
   const int b = (u >> 2) / qts;
   const int Nq = p.Nq[side], Nk = p.Nk[side];
-  const long long qrow = p.q_row0[side] + (long long)b * Nq + qblk * 256;
+  const long long qrow = p.q_row0[side] + (long long)b * Nq + qblk * (NT * 128);
   const long long krow = p.k_row0[side] + (long long)b * Nk;
   const int n_kv = (Nk + 127) / 128;
 
@@ -62,7 +64,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
       mbar_init(&bars->kv_full[s], 1);
       mbar_init(&bars->kv_empty[s], 1);
     }
-    for (int t = 0; t < 2; t++) {
+    for (int t = 0; t < NT; t++) {
       mbar_init(&bars->s_full[t], 1);
       mbar_init(&bars->p_full[t], 4);
       mbar_init(&bars->o_full[t], 1);
@@ -70,19 +72,18 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(&bars->tmem_base);
+  if (warp == 1) tmem_alloc<NT * 256>(&bars->tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-  constexpr uint32_t COL_S = 0, COL_O = 256, COL_P = 384;
+  constexpr uint32_t COL_S = 0, COL_O = NT * 128, COL_P = NT * 128 + NT * 64;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bars->q_full, 2 * TILE_BYTES);
-      tma_load_2d(sQ, &map, &bars->q_full, head * 64, (int)qrow);
-      tma_load_2d(sQ + TILE_BYTES, &map, &bars->q_full, head * 64, (int)qrow + 128);
+      mbar_arrive_expect_tx(&bars->q_full, NT * TILE_BYTES);
+      for (int t = 0; t < NT; t++) tma_load_2d(sQ + t * TILE_BYTES, &map, &bars->q_full, head * 64, (int)qrow + t * 128);
       for (int j = 0; j < n_kv; j++) {
         const int s = j % KV_STAGES;
         mbar_wait(&bars->kv_empty[s], ((j / KV_STAGES) & 1) ^ 1);
@@ -96,16 +97,16 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);  // S = Q K^T : B = K tile, K-major
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);   // O = P V   : B = V tile, MN-major
-      uint64_t q_desc[2], k_desc[KV_STAGES], v_desc[KV_STAGES];
+      uint64_t q_desc[NT], k_desc[KV_STAGES], v_desc[KV_STAGES];
 #pragma unroll
-      for (int t = 0; t < 2; t++) q_desc[t] = umma_desc_sw128(smem_u32(sQ + t * TILE_BYTES), 16, 1024);
+      for (int t = 0; t < NT; t++) q_desc[t] = umma_desc_sw128(smem_u32(sQ + t * TILE_BYTES), 16, 1024);
 #pragma unroll
       for (int s = 0; s < KV_STAGES; s++) {
         k_desc[s] = umma_desc_sw128(smem_u32(sK + s * TILE_BYTES), 16, 1024);
         v_desc[s] = umma_desc_sw128(smem_u32(sV + s * TILE_BYTES), 1024, 1024);
       }
       auto issue_s = [&](int t, int stage) {
-        const uint64_t ad = q_desc[t], bd = stage == 0 ? k_desc[0] : (stage == 1 ? k_desc[1] : k_desc[2]);
+        const uint64_t ad = (NT == 1 || t == 0) ? q_desc[0] : q_desc[NT - 1], bd = stage == 0 ? k_desc[0] : (stage == 1 ? k_desc[1] : k_desc[2]);
 #pragma unroll
         for (int k = 0; k < 4; k++)
           umma_ss(tmem + COL_S + t * 128, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc_s,
@@ -115,8 +116,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
       mbar_wait(&bars->q_full, 0);
       mbar_wait(&bars->kv_full[0], 0);
       tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
+      for (int t = 0; t < NT; t++) issue_s(t, 0);
       for (int j = 0; j < n_kv; j++) {
         const int s = j % KV_STAGES;
         // (1) as soon as a warpgroup has pulled S_t(j) into registers its TMEM region is free again: issue
@@ -124,14 +124,14 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
         if (j + 1 < n_kv) {
           const int s1 = (j + 1) % KV_STAGES;
           mbar_wait(&bars->kv_full[s1], ((j + 1) / KV_STAGES) & 1);
-          for (int t = 0; t < 2; t++) {
+          for (int t = 0; t < NT; t++) {
             mbar_wait(&bars->s_free[t], j & 1);
             tc_fence_after();
             issue_s(t, s1);
           }
         }
         // (2) P_t(j) written (much later): accumulate O_t += P_t V_j
-        for (int t = 0; t < 2; t++) {
+        for (int t = 0; t < NT; t++) {
           mbar_wait(&bars->p_full[t], j & 1);
           tc_fence_after();
           const uint64_t vd = s == 0 ? v_desc[0] : (s == 1 ? v_desc[1] : v_desc[2]);
@@ -149,7 +149,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
     const int t = (warp - 2) >> 2;  // query tile of this warpgroup
     const int quad = warp & 3;      // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
-    const int qi = qblk * 256 + t * 128 + row_in_tile;  // query index inside the pair
+    const int qi = qblk * (NT * 128) + t * 128 + row_in_tile;  // query index inside the pair
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     const float c = 0.125f * 1.4426950408889634f;  // log2(e) / sqrt(64)
     float m_used = -INFINITY, l_run = 0.f;
@@ -257,8 +257,24 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem);
+  if (warp == 1) tmem_dealloc<NT * 256>(tmem);
 }
+
+template <int NT>
+int launch_att(const TcAttn& p, const CUtensorMap& map, cudaStream_t st) {
+  const int qt0 = cdiv(p.Nq[0], NT * 128), qt1 = p.Nq[1] > 0 ? cdiv(p.Nq[1], NT * 128) : 0;
+  const int units0 = p.B * 4 * qt0, units1 = p.B * 4 * qt1;
+  const size_t smem = (size_t)(NT + 2 * KV_STAGES) * TILE_BYTES + sizeof(AttBars) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    SFM_CUDA(cudaFuncSetAttribute(tc_attention_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  tc_attention_kernel<NT><<<units0 + units1, AttCfg<NT>::THREADS, smem, st>>>(map, p, units0, qt0, qt1 > 0 ? qt1 : 1);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
 
 }  // namespace
 
@@ -266,17 +282,9 @@ int tc_attention(const TcAttn& p, cudaStream_t st) {
   SFM_REQUIRE(p.B > 0 && p.Nq[0] > 0 && p.Nk[0] > 0 && p.Nq[1] >= 0, "tc_attention: bad dims");
   CUtensorMap map;
   SFM_TRY(make_tmap_bf16(&map, p.qkv, p.rows_total, 768, 768, 128));
-  const int qt0 = cdiv(p.Nq[0], 256), qt1 = p.Nq[1] > 0 ? cdiv(p.Nq[1], 256) : 0;
-  const int units0 = p.B * 4 * qt0, units1 = p.B * 4 * qt1;
-  const size_t smem = (size_t)(2 + 2 * KV_STAGES) * TILE_BYTES + sizeof(AttBars) + 1024;
-  static bool configured = false;
-  if (!configured) {
-    SFM_CUDA(cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
-  tc_attention_kernel<<<units0 + units1, ATT_THREADS, smem, st>>>(map, p, units0, qt0, qt1 > 0 ? qt1 : 1);
-  SFM_LAUNCH_CHECK();
-  return SFM_OK;
+  static int nt = getenv("SFM_ATT_NT") ? atoi(getenv("SFM_ATT_NT")) : 2;
+  if (nt == 1) return launch_att<1>(p, map, st);
+  return launch_att<2>(p, map, st);
 }
 
 }  // namespace tc

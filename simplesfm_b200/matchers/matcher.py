@@ -76,7 +76,7 @@ class Matcher(object):
                  precision: str = 'fp32',
                  device: str = 'cuda',
                  shard_pairs: bool = True,
-                 fuse_chunks: int = 8,
+                 fuse_chunks: int = 16,
                  superpoint_precision: str = 'fp32'):
 
         self.matcher_type = matcher_type
