@@ -134,6 +134,12 @@ SFM_API int sfm_superglue_forward(sfm_handle_t h,
 SFM_API int sfm_superglue_tap(int B, int K0, int K1, int precision, int chunk_groups, int which, void* workspace,
                       size_t workspace_bytes, float** out_ptr, size_t* out_floats);
 
+/* attention (superglue.py:85-89) in the reference's own layout, fp32: query (B,64,4,N), key/value (B,64,4,M)
+ * -> out (B,64,4,N) and, when prob != NULL, the materialised softmax prob (B,4,N,M). */
+SFM_API size_t sfm_attention_workspace_bytes(int B, int N, int M);
+SFM_API int sfm_attention(const float* query, const float* key, const float* value, int B, int N, int M, float* out,
+                          float* prob, void* workspace, size_t workspace_bytes, void* stream);
+
 /* log_optimal_transport (superglue.py:151-171): scores (B,N,M) -> Z (B,N+1,M+1) */
 SFM_API size_t sfm_sinkhorn_workspace_bytes(int B, int N, int M);
 SFM_API int sfm_log_optimal_transport(const float* scores, int B, int N, int M, float alpha, int iters, float* Z,

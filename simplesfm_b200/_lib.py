@@ -55,6 +55,9 @@ _SIGNATURES = {
                                         C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfm_superglue_tap": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "sfm_attention_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
+    "sfm_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfm_sinkhorn_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "sfm_log_optimal_transport": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p,
                                             C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -484,6 +484,62 @@ int sfm_sinkhorn_match_scaled(float* scores, int B, int N, int M, float alpha, i
                         mscores0, mscores1, (cudaStream_t)stream);
 }
 
+// ---- stand-alone attention in the reference layout (superglue.py:85-89), fp32 FFMA path
+namespace {
+struct AttBuffers { float *qT, *kT, *vT, *S, *oT; int ldS; };
+size_t att_carve(int B, int N, int M, void* ws, size_t ws_bytes, AttBuffers& b) {
+  Arena a(ws, ws_bytes);
+  b.ldS = (M + 3) / 4 * 4;
+  b.qT = a.get<float>((size_t)B * 4 * N * 64);
+  b.kT = a.get<float>((size_t)B * 4 * M * 64);
+  b.vT = a.get<float>((size_t)B * 4 * M * 64);
+  b.oT = a.get<float>((size_t)B * 4 * N * 64);
+  b.S = a.get<float>((size_t)B * 4 * N * b.ldS);
+  return a.off;
+}
+}  // namespace
+
+size_t sfm_attention_workspace_bytes(int B, int N, int M) {
+  if (B < 0 || N < 0 || M < 0) return 0;
+  AttBuffers b;
+  return att_carve(B, N, M, nullptr, 0, b);
+}
+
+int sfm_attention(const float* query, const float* key, const float* value, int B, int N, int M, float* out,
+                  float* prob, void* ws, size_t ws_bytes, void* stream) {
+  SFM_REQUIRE(B >= 0 && N >= 0 && M > 0, "sfm_attention: B, N >= 0 and M > 0 required (B=%d N=%d M=%d)", B, N, M);
+  if (B == 0 || N == 0) return SFM_OK;
+  SFM_REQUIRE(query && key && value && out && ws, "sfm_attention: NULL argument");
+  SFM_REQUIRE(B * 4 <= 65535, "sfm_attention: B too large");
+  AttBuffers b;
+  size_t need = att_carve(B, N, M, ws, ws_bytes, b);
+  SFM_REQUIRE(ws_bytes >= need, "sfm_attention: workspace too small (%zu < %zu)", ws_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  // (B,64,4,L): element (b,d,h,l) at b*256L + d*4L + h*L + l  ->  [b][h][l][d]
+  SFM_TRY(transpose_batched_f32(query, b.qT, B * 4, 4, 64, N, 4ll * N, 64, 256ll * N, N, 256ll * N, 64ll * N, st));
+  SFM_TRY(transpose_batched_f32(key, b.kT, B * 4, 4, 64, M, 4ll * M, 64, 256ll * M, M, 256ll * M, 64ll * M, st));
+  SFM_TRY(transpose_batched_f32(value, b.vT, B * 4, 4, 64, M, 4ll * M, 64, 256ll * M, M, 256ll * M, 64ll * M, st));
+  GemmF32 g;
+  g.A = b.qT; g.lda = 64;
+  g.B = b.kT; g.ldb = 64;
+  g.C = b.S; g.ldc = b.ldS;
+  g.M = N; g.N = M; g.K = 64; g.alpha = 0.125f;
+  g.batch = B * 4; g.nb1 = 1;
+  g.sA0 = 64ll * N; g.sB0 = 64ll * M; g.sC0 = (long long)N * b.ldS;
+  SFM_TRY(gemm_f32_nt(g, st));
+  SFM_TRY(softmax_rows_f32(b.S, (long long)B * 4 * N, M, b.ldS, st));
+  if (prob) SFM_TRY(copy_rows_f32(b.S, prob, (long long)B * 4 * N, M, b.ldS, M, st));
+  GemmF32 p;
+  p.A = b.S; p.lda = b.ldS;
+  p.B = b.vT; p.ldb = 64;
+  p.C = b.oT; p.ldc = 64;
+  p.M = N; p.N = 64; p.K = M;
+  p.batch = B * 4; p.nb1 = 1;
+  p.sA0 = (long long)N * b.ldS; p.sB0 = 64ll * M; p.sC0 = 64ll * N;
+  SFM_TRY(gemm_f32_nn(p, st));
+  return transpose_batched_f32(b.oT, out, B * 4, 4, N, 64, 64, 4ll * N, 256ll * N, 64ll * N, 256ll * N, N, st);
+}
+
 int sfm_compact_matches(const int64_t* matches0, int B, int K0, uint32_t* tables, int* lengths, void* stream) {
   SFM_REQUIRE(B == 0 || (matches0 && tables && lengths), "sfm_compact_matches: NULL argument");
   return compact_matches((const long long*)matches0, B, K0, tables, lengths, (cudaStream_t)stream);

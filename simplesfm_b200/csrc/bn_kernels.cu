@@ -131,7 +131,7 @@ __device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, flo
 }
 
 __global__ void __launch_bounds__(256) bn_final_kernel(const float* __restrict__ partial, int C, BnGroups gr, int nb0,
-                                                       int nb1, const float* __restrict__ gamma,
+                                                       int nb1, int rb, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, float eps,
                                                        float* __restrict__ scale, float* __restrict__ shift) {
   const int g = blockIdx.y;   // side * G + group
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) bn_final_kernel(const float* __restrict__
   const long long n_total = (side ? gr.T1 : gr.T0) / gr.G;
   float mean = 0.f, m2 = 0.f, n = 0.f;
   for (int b = lane; b < nb; b += 32) {
-    const float rows = (float)min((long long)RB, n_total - (long long)b * RB);
+    const float rows = (float)min((long long)rb, n_total - (long long)b * rb);
     const float2 pm = *reinterpret_cast<const float2*>(partial + ((long long)(b0 + b) * C + c) * 2);
     chan_merge(n, mean, m2, rows, pm.x, pm.y);
   }
@@ -164,6 +164,48 @@ __global__ void __launch_bounds__(256) bn_final_kernel(const float* __restrict__
   }
   if (lane == 0) {
     const float var = n > 0.f ? m2 / n : 0.f;
+    const float a = gamma[c] * (1.0f / sqrtf(var + eps));
+    scale[g * C + c] = a;
+    shift[g * C + c] = beta[c] - mean * a;
+  }
+}
+
+// Same result for partials whose blocks all hold exactly `rb` rows (what the GEMM epilogue writes): two
+// coalesced passes, no divisions in the loop.  CTA = (32 channels, group); lane = channel, warps stride blocks.
+__global__ void __launch_bounds__(256) bn_final_equal_kernel(const float* __restrict__ partial, int C, BnGroups gr,
+                                                             int nb0, int nb1, int rb, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps,
+                                                             float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ float red[8][32];
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int side = g >= gr.G ? 1 : 0, grp = side ? g - gr.G : g;
+  const int nb = side ? nb1 : nb0;
+  const long long b0 = side ? (long long)gr.G * nb0 + (long long)grp * nb1 : (long long)grp * nb0;
+  const float2* src = reinterpret_cast<const float2*>(partial) + b0 * C + c;
+  float s = 0.f;
+  for (int b = w; b < nb; b += 8) s += src[(long long)b * C].x;
+  red[w][lane] = s;
+  __syncthreads();
+  float mean = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; k++) mean += red[k][lane];
+  mean /= (float)nb;
+  __syncthreads();
+  float q = 0.f;
+  for (int b = w; b < nb; b += 8) {
+    const float2 pm = src[(long long)b * C];
+    const float d = pm.x - mean;
+    q += fmaf(d * d, (float)rb, pm.y);
+  }
+  red[w][lane] = q;
+  __syncthreads();
+  if (w == 0) {
+    float m2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) m2 += red[k][lane];
+    const float var = m2 / ((float)nb * (float)rb);
     const float a = gamma[c] * (1.0f / sqrtf(var + eps));
     scale[g * C + c] = a;
     shift[g * C + c] = beta[c] - mean * a;
@@ -247,8 +289,23 @@ int bn_train_stats(const T* X, int ld, int C, const BnGroups& g, const float* ga
   } else {
     bn_partial_kernel<T><<<total, 256, 0, st>>>(X, ld, C, g, nb0, nb1, partial);
   }
-  bn_final_kernel<<<dim3(cdiv(C, 8), 2 * g.G), 256, 0, st>>>(partial, C, g, nb0, nb1, gamma, beta, eps, scale, shift);
+  bn_final_kernel<<<dim3(cdiv(C, 8), 2 * g.G), 256, 0, st>>>(partial, C, g, nb0, nb1, RB, gamma, beta, eps, scale, shift);
   SFM_LAUNCH_CHECK_N(2);
+  return SFM_OK;
+}
+
+int bn_finalize(const float* partial, int rb, int C, const BnGroups& g, const float* gamma, const float* beta, float eps,
+                float* scale, float* shift, cudaStream_t st) {
+  SFM_REQUIRE(g.G >= 1 && (g.T0 / g.G) % rb == 0 && (g.T1 / g.G) % rb == 0 && g.T0 % g.G == 0 && g.T1 % g.G == 0,
+              "bn_finalize: statistic groups must be whole %d-row blocks", rb);
+  const int nb0 = (int)(g.T0 / g.G / rb), nb1 = (int)(g.T1 / g.G / rb);
+  if (g.G * (nb0 + nb1) == 0) return SFM_OK;
+  if (C % 32 == 0 && nb0 > 0 && nb1 > 0)
+    bn_final_equal_kernel<<<dim3(C / 32, 2 * g.G), 256, 0, st>>>(partial, C, g, nb0, nb1, rb, gamma, beta, eps, scale,
+                                                                  shift);
+  else
+    bn_final_kernel<<<dim3(cdiv(C, 8), 2 * g.G), 256, 0, st>>>(partial, C, g, nb0, nb1, rb, gamma, beta, eps, scale, shift);
+  SFM_LAUNCH_CHECK();
   return SFM_OK;
 }
 

@@ -19,6 +19,10 @@ int bn_stat_blocks(const BnGroups& g);
 template <typename T>
 int bn_train_stats(const T* X, int ld, int C, const BnGroups& g, const float* gamma, const float* beta, float eps,
                    float* partial, float* scale, float* shift, cudaStream_t st);
+// scale/shift from partials produced elsewhere (the tcgen05 GEMM epilogue): [rows / rb, C, 2] (mean, centred M2)
+// per rb-row block, block index = global row / rb
+int bn_finalize(const float* partial, int rb, int C, const BnGroups& g, const float* gamma, const float* beta, float eps,
+                float* scale, float* shift, cudaStream_t st);
 template <typename T>
 int bn_apply_relu(T* X, int ld, int C, const BnGroups& g, const float* scale, const float* shift, cudaStream_t st);
 

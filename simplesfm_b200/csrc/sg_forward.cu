@@ -1,5 +1,6 @@
 // SuperGlue.forward orchestration (reference simple_sfm/models/superglue.py:235-290).
 // Token-major activations: X [T0 + T1, 256], side-0 tokens (b*K0 + k) first, then side 1.
+#include <algorithm>
 #include "context.cuh"
 #include "gemm_f32.cuh"
 #include "sg_kernels.cuh"
@@ -27,7 +28,9 @@ int carve(Arena& a, const SgCall& c, SgBuffers& b) {
   b.t0 = a.get<float>(T * 256);   // keypoint-encoder ping-pong (fp32 SIMT on both precision paths)
   b.t1 = a.get<float>(T * 256);
   const int G = c.groups > 0 ? c.groups : 1;
-  b.bn_part = a.get<float>((size_t)bn_stat_blocks(BnGroups{T0, T1, G}) * 512 * 2);
+  // BatchNorm partial moments: 64-row blocks of the stand-alone kernels, or 32-row blocks written by the
+  // tcgen05 GEMM epilogue (tc_path.cu)
+  b.bn_part = a.get<float>(std::max((size_t)bn_stat_blocks(BnGroups{T0, T1, G}), (size_t)((T0 + T1) / 32 + 1)) * 512 * 2);
   b.bn_scale = a.get<float>((size_t)2 * G * 512);
   b.bn_shift = a.get<float>((size_t)2 * G * 512);
   if (c.precision == 0) {   // fp32-path activations

@@ -684,6 +684,54 @@ int sg_frontend(const float* desc, long long desc_img_stride, int ldk, const flo
   return SFM_OK;
 }
 
+namespace {
+// [batch][R][C] (row stride ldi, batch stride = bsi0 * (z / nb1) + bsi1 * (z % nb1)) -> [batch][C][R] likewise
+__global__ void transpose_batched_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C,
+                                         long long ldi, long long ldo, int nb1, long long bsi0, long long bsi1,
+                                         long long bso0, long long bso1) {
+  __shared__ float tile[32][33];
+  const int z = blockIdx.z;
+  const float* src = in + bsi0 * (z / nb1) + bsi1 * (z % nb1);
+  float* dst = out + bso0 * (z / nb1) + bso1 * (z % nb1);
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? src[r * ldi + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) dst[c * ldo + r] = tile[threadIdx.x][i];
+  }
+}
+__global__ void copy_rows_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int M,
+                                 int ldi, int ldo) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * M) return;
+  long long r = i / M;
+  int c = (int)(i - r * M);
+  out[r * ldo + c] = in[r * ldi + c];
+}
+}  // namespace
+
+int transpose_batched_f32(const float* in, float* out, int batch, int nb1, int R, int C, long long ldi,
+                          long long ldo, long long bsi0, long long bsi1, long long bso0, long long bso1,
+                          cudaStream_t st) {
+  if (batch == 0 || R == 0 || C == 0) return SFM_OK;
+  SFM_REQUIRE(batch <= 65535 && cdiv(R, 32) <= 65535, "transpose: batch/rows too large");
+  dim3 grid(cdiv(C, 32), cdiv(R, 32), batch), block(32, 8);
+  transpose_batched_kernel<<<grid, block, 0, st>>>(in, out, R, C, ldi, ldo, nb1, bsi0, bsi1, bso0, bso1);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+int copy_rows_f32(const float* in, float* out, long long rows, int M, int ldi, int ldo, cudaStream_t st) {
+  if (rows == 0 || M == 0) return SFM_OK;
+  copy_rows_kernel<<<(unsigned)cdiv(rows * M, 256), 256, 0, st>>>(in, out, rows, M, ldi, ldo);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
 int softmax_rows_f32(float* S, long long rows, int M, int ld, cudaStream_t st) {
   if (rows == 0 || M == 0) return SFM_OK;
   softmax_rows_kernel<<<cdiv(rows * 32, 256), 256, 0, st>>>(S, rows, M, ld);

@@ -16,6 +16,11 @@ int sg_frontend(const float* desc, long long desc_img_stride, int ldk, const flo
 
 // in-place softmax over the last dim of [rows, M] (ld)
 int softmax_rows_f32(float* S, long long rows, int M, int ld, cudaStream_t st);
+// batched 2-D transpose, batch index z -> offsets bs?0 * (z / nb1) + bs?1 * (z % nb1)
+int transpose_batched_f32(const float* in, float* out, int batch, int nb1, int R, int C, long long ldi,
+                          long long ldo, long long bsi0, long long bsi1, long long bso0, long long bso1,
+                          cudaStream_t st);
+int copy_rows_f32(const float* in, float* out, long long rows, int M, int ldi, int ldo, cudaStream_t st);
 
 // ---- optimal transport + matching (superglue.py:142-171, 273-283)
 struct SinkhornArgs {

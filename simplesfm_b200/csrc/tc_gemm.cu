@@ -28,6 +28,7 @@ constexpr int GEMM_THREADS = 320;
 struct Barriers {
   uint64_t w_full, w_empty;
   uint64_t a_full[STAGES], a_empty[STAGES];
+  uint64_t a_ready[STAGES];   // XF only: the stage has been normalised in place and is visible to the MMA
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
@@ -54,8 +55,28 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int BN, int KBLOCKS>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+// y = relu(x * a + b) on a packed bf16 pair
+__device__ __forceinline__ uint32_t bn_relu_pair(uint32_t x, float a0, float b0, float a1, float b1) {
+  const float lo = fmaxf(fmaf(__uint_as_float(x << 16), a0, b0), 0.f);
+  const float hi = fmaxf(fmaf(__uint_as_float(x & 0xffff0000u), a1, b1), 0.f);
+  return pack_bf16(lo, hi);
+}
+
+// XF = true adds four "transform" warps that apply the train-mode BatchNorm affine + ReLU
+// (superglue.py:56-58) to every A stage in shared memory between the TMA landing and the MMA, so the
+// normalised hidden activations never make a round trip through HBM.
+template <int BN, int KBLOCKS, bool XF>
+__global__ void __launch_bounds__(XF ? GEMM_THREADS + 128 : GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO, TcGemm p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -88,6 +109,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&bars->a_full[s], 1);
       mbar_init(&bars->a_empty[s], 1);
+      mbar_init(&bars->a_ready[s], 4);
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(&bars->acc_full[b], 1);
@@ -158,7 +180,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const uint32_t d_tmem = tmem_base + buf * BN;
 #pragma unroll
           for (int kb = 0; kb < KBLOCKS; kb++) {
-            DBG_WAIT(0, mbar_wait(&bars->a_full[stage], phase));
+            DBG_WAIT(0, mbar_wait(XF ? &bars->a_ready[stage] : &bars->a_full[stage], phase));
             tc_fence_after();
             const uint64_t ad = umma_desc_advance(a_desc0, stage * A_STAGE_BYTES), bd = w_desc[kb];
 #pragma unroll
@@ -173,6 +195,78 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           umma_commit(&bars->acc_full[buf]);
         }
         umma_commit(&bars->w_empty);
+      }
+    }
+  } else if (XF && warp >= 10) {
+    // ------------------------------------------------------------------ A transform: relu(a * scale + shift)
+    // thread -> one fixed 16-byte chunk column (8 channels) and 8 rows of the stage, so a stage needs only
+    // 16 scale/shift values per thread; they are fetched for the NEXT stage before waiting on the current one.
+    // A quarter warp covers one 128-byte row: conflict-free against the 128B swizzle.
+    const int t = threadIdx.x - GEMM_THREADS;
+    const int j = t & 7, rbase = t >> 3;       // logical chunk, first row (rows rbase + 16 * i)
+    int stage = 0, phase = 0;
+    auto group_ptr = [&](int b, int mt, const float4*& sc, const float4*& sh) {
+      const long long row0 = (long long)b * p.a_row_stride + (long long)mt * BM;
+      const int g = row0 >= p.xf_T0 ? p.xf_G + (int)((row0 - p.xf_T0) / p.xf_rows1) : (int)(row0 / p.xf_rows0);
+      sc = reinterpret_cast<const float4*>(p.xf_scale + (long long)g * p.K);
+      sh = reinterpret_cast<const float4*>(p.xf_shift + (long long)g * p.K);
+    };
+    float4 a0, a1, b0, b1;        // scale / shift of the current stage's 8 channels
+    float4 na0, na1, nb0, nb1;    // ... of the next stage
+    bool first = true;
+    for (int pj = slot; pj < n_pj; pj += n_slots) {
+      const int b = pj / p.num_panels;
+      for (int mt = sub; mt < p.num_m_tiles; mt += p.cpp) {
+        const float4 *sc, *sh;
+        group_ptr(b, mt, sc, sh);
+        if (first) {
+          na0 = __ldg(sc + j * 2); na1 = __ldg(sc + j * 2 + 1);
+          nb0 = __ldg(sh + j * 2); nb1 = __ldg(sh + j * 2 + 1);
+          first = false;
+        }
+#pragma unroll
+        for (int kb = 0; kb < KBLOCKS; kb++) {
+          a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
+          {
+            // prefetch the next stage's coefficients (next k-block, or k-block 0 of this CTA's next tile)
+            const float4 *nsc = sc, *nsh = sh;
+            int nkb = kb + 1;
+            if (nkb == KBLOCKS) {
+              nkb = 0;
+              if (mt + p.cpp < p.num_m_tiles)
+                group_ptr(b, mt + p.cpp, nsc, nsh);
+              else if (pj + n_slots < n_pj)
+                group_ptr((pj + n_slots) / p.num_panels, sub, nsc, nsh);
+              // else: last stage of this CTA, the (unused) prefetch re-reads the current group
+            }
+            na0 = __ldg(nsc + nkb * 16 + j * 2); na1 = __ldg(nsc + nkb * 16 + j * 2 + 1);
+            nb0 = __ldg(nsh + nkb * 16 + j * 2); nb1 = __ldg(nsh + nkb * 16 + j * 2 + 1);
+          }
+          mbar_wait(&bars->a_full[stage], phase);
+          const uint32_t base = smem_u32(sA + stage * A_STAGE_BYTES);
+          uint4 raw[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int r = rbase + 16 * i;
+            raw[i] = lds128u(base + r * 128 + ((j ^ (r & 7)) << 4));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int r = rbase + 16 * i;
+            raw[i].x = bn_relu_pair(raw[i].x, a0.x, b0.x, a0.y, b0.y);
+            raw[i].y = bn_relu_pair(raw[i].y, a0.z, b0.z, a0.w, b0.w);
+            raw[i].z = bn_relu_pair(raw[i].z, a1.x, b1.x, a1.y, b1.y);
+            raw[i].w = bn_relu_pair(raw[i].w, a1.z, b1.z, a1.w, b1.w);
+            sts128(base + r * 128 + ((j ^ (r & 7)) << 4), raw[i].x, raw[i].y, raw[i].z, raw[i].w);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->a_ready[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
       }
     }
   } else {
@@ -302,6 +396,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (col < p.N && !(p.dbg_flags & 4)) tma_store_2d(&mapO, slab, col, p.out_row_base + b * p.out_row_stride + mt * BM);
                 tma_store_commit();
               }
+              if (p.stat_partial != nullptr) {
+                // BatchNorm batch statistics of this slab (bf16-rounded values, as stored): per 32-row block and
+                // column the mean and centred second moment; lane = column pair, warp = row quarter.
+                const int w4 = wg_tid >> 5;
+                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+                for (int rr = 0; rr < 32; rr++) {
+                  const int r = w4 * 32 + rr;
+                  const uint32_t x = lds32(slab_u32 + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
+                  const float lo = __uint_as_float(x << 16), hi = __uint_as_float(x & 0xffff0000u);
+                  s0 += lo; s1 += hi;
+                  q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
+                }
+                const int col = panel * BN + wg * HALF + (c >> 1) * 64 + lane * 2;
+                if (col < p.N) {
+                  const float m0 = s0 * (1.f / 32.f), m1 = s1 * (1.f / 32.f);
+                  const long long blk = ((long long)b * p.a_row_stride + (long long)mt * BM) / 32 + w4;
+                  *reinterpret_cast<float4*>(p.stat_partial + (blk * p.N + col) * 2) =
+                      make_float4(m0, fmaxf(q0 - s0 * m0, 0.f), m1, fmaxf(q1 - s1 * m1, 0.f));
+                }
+              }
             }
           }
         }
@@ -321,7 +436,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-template <int BN, int KBLOCKS>
+template <int BN, int KBLOCKS, bool XF = false>
 int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mW,
            const CUtensorMap& mO, int num_sms, cudaStream_t st) {
   TcGemm p = p_in;
@@ -338,7 +453,7 @@ int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, co
                       sizeof(Barriers) + 1024;
   static bool configured = false;
   if (!configured) {
-    SFM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, KBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SFM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, KBLOCKS, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   static long long* dbg = nullptr;
@@ -347,7 +462,7 @@ int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, co
   p.dbg = want_dbg ? dbg : nullptr;
   p.dbg_flags = getenv("SFM_TC_FLAGS") ? atoi(getenv("SFM_TC_FLAGS")) : 0;
   if (want_dbg) cudaMemsetAsync(dbg, 0, 148 * 3 * 6 * sizeof(long long), st);
-  tc_gemm_kernel<BN, KBLOCKS><<<n_slots * cpp, GEMM_THREADS, smem, st>>>(mA, mA2, mW, mO, p);
+  tc_gemm_kernel<BN, KBLOCKS, XF><<<n_slots * cpp, XF ? GEMM_THREADS + 128 : GEMM_THREADS, smem, st>>>(mA, mA2, mW, mO, p);
   SFM_LAUNCH_CHECK();
   if (want_dbg) {
     static long long host[148 * 3 * 6];
@@ -412,6 +527,11 @@ int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
   SFM_REQUIRE(p.K1 % 64 == 0 && p.K1 > 0 && p.K1 <= p.K, "tc_gemm: bad split point");
   SFM_REQUIRE(p.out_h == nullptr || (p.out_h_ld % 8 == 0 && p.batch == 1 && p.M == p.a_rows),
               "tc_gemm: bf16 output needs ld %% 8 == 0 and an unbatched problem");
+  SFM_REQUIRE(p.stat_partial == nullptr || (p.out_h != nullptr && p.M % 128 == 0 && p.N % 64 == 0 && !p.accumulate_f),
+              "tc_gemm: fused BatchNorm statistics need a bf16 output, M %% 128 == 0 and N %% 64 == 0");
+  SFM_REQUIRE(p.xf_scale == nullptr || (p.K == 512 && p.K1 == p.K && p.xf_shift != nullptr && p.xf_rows0 % 128 == 0 &&
+                                        p.xf_rows1 % 128 == 0 && p.xf_T0 % 128 == 0 && p.xf_G >= 1),
+              "tc_gemm: fused BatchNorm apply needs K = 512 and statistic groups that are whole 128-row tiles");
   CUtensorMap mA, mA2, mW, mO;
   SFM_TRY(make_tmap_bf16(&mA, p.A, p.a_rows, p.K1, p.lda, BM));
   if (p.K1 < p.K)
@@ -438,6 +558,7 @@ int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
     if (wide) return launch<256, 4>(q, mA, mA2, mW, mO, num_sms, st);
     return launch<128, 4>(q, mA, mA2, mW, mO, num_sms, st);
   }
+  if (p.xf_scale != nullptr) return launch<128, 8, true>(q, mA, mA2, mW, mO, num_sms, st);
   return launch<128, 8>(q, mA, mA2, mW, mO, num_sms, st);
 }
 

@@ -1,6 +1,7 @@
 // SuperGlue GNN on the bf16 tcgen05 path (reference simple_sfm/models/superglue.py:254-265).
 // fp32 master copy of the residual stream X, bf16 shadow for the tensor-core operands.
 #include "tc_path.cuh"
+#include <stdlib.h>
 #include "bn_kernels.cuh"
 #include "gemm_f32.cuh"
 
@@ -82,6 +83,11 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
     g4.out_h = b.xh; g4.out_h_ld = 256; g4.out_f = X; g4.out_f_ld = 256; g4.accumulate_f = 1;
     SFM_TRY(tc_gemm(g4, sms, st));
   }
+  const BnGroups gr{T0, T1, c.groups > 0 ? c.groups : 1};
+  // fusion needs every statistic group to be whole 128-row GEMM tiles; ragged keypoint counts take the
+  // stand-alone BatchNorm kernels
+  const bool fuse_bn = train && T0 % gr.G == 0 && T1 % gr.G == 0 && (T0 / gr.G) % 128 == 0 && (T1 / gr.G) % 128 == 0 &&
+                       T0 > 0 && T1 > 0 && getenv("SFM_NO_BN_FUSION") == nullptr;
   for (int l = 0; l < 18; l++) {
     const SgLayer& L = w.L[l];
     const bool cross = l & 1;
@@ -97,10 +103,40 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
       SFM_TRY(tc_attention(a, st));
     }
     // the merge conv is folded into the MLP input weights (W1c), so the attention output feeds the MLP directly
+    if (train && fuse_bn) {
+      // BatchNorm fused into the two GEMMs around it: MLP1's epilogue emits the per-block moments, a tiny
+      // kernel turns them into scale/shift per statistic group, MLP2 normalises + ReLUs its A tiles in smem
+      {
+        ProfScope ps(h, SFM_PROF_LINEAR, st);
+        TcGemm g;
+        g.A = b.xh; g.lda = 256; g.A2 = b.msgp; g.lda2 = 256; g.a_rows = T;
+        g.W = L.W1c_h; g.ldw = 512; g.w_rows = 512;
+        g.M = (int)T; g.N = 512; g.K = 512; g.K1 = 256;
+        g.bias = L.b1c;
+        g.out_h = b.hid; g.out_h_ld = 512;
+        g.stat_partial = b.bn_part;
+        SFM_TRY(tc_gemm(g, sms, st));
+      }
+      {
+        ProfScope ps(h, SFM_PROF_OTHER, st);
+        SFM_TRY(bn_finalize(b.bn_part, 32, 512, gr, L.bn1.gamma, L.bn1.beta, 1e-5f, b.bn_scale, b.bn_shift, st));
+      }
+      ProfScope ps(h, SFM_PROF_LINEAR, st);
+      TcGemm g;
+      g.A = b.hid; g.lda = 512; g.a_rows = T;
+      g.W = L.W2_h; g.ldw = 512; g.w_rows = 256;
+      g.M = (int)T; g.N = 256; g.K = 512; g.K1 = 512;
+      g.bias = L.b2;
+      g.out_h = b.xh; g.out_h_ld = 256;
+      g.out_f = X; g.out_f_ld = 256; g.accumulate_f = 1;
+      g.xf_scale = b.bn_scale; g.xf_shift = b.bn_shift;
+      g.xf_T0 = T0; g.xf_G = gr.G; g.xf_rows0 = T0 / gr.G; g.xf_rows1 = T1 / gr.G;
+      SFM_TRY(tc_gemm(g, sms, st));
+      continue;
+    }
     if (train) {
       SFM_TRY(linear(b.xh, 256, b.msgp, 256, 512, 256, L.W1c_h, 512, L.b1c, 0, b.hid, 512, nullptr, 0));
       ProfScope ps(h, SFM_PROF_OTHER, st);
-      const BnGroups gr{T0, T1, c.groups > 0 ? c.groups : 1};
       SFM_TRY(bn_train_stats<__nv_bfloat16>(b.hid, 512, 512, gr, L.bn1.gamma, L.bn1.beta, 1e-5f, b.bn_part, b.bn_scale,
                                             b.bn_shift, st));
       SFM_TRY(bn_apply_relu<__nv_bfloat16>(b.hid, 512, 512, gr, b.bn_scale, b.bn_shift, st));

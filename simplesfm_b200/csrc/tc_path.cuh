@@ -43,6 +43,16 @@ struct TcGemm {
   float* out_f = nullptr;
   long long out_f_ld = 0, out_f_bstride = 0;
   int accumulate_f = 0;  // out_f += result (residual stream); out_h then holds bf16(out_f)
+  // fused train-mode BatchNorm (both optional):
+  //  stat_partial: the epilogue also writes, per 32-row block and output column, (mean, centred M2) of the
+  //                bf16 output -> [M/32, N, 2] floats, block index = global row / 32 (feeds bn_finalize)
+  //  xf_*:         A is normalised on the fly, a <- relu(a * scale[g] + shift[g]) with g the statistic group of
+  //                the tile's rows (side 0 rows [0,xf_T0) in groups of xf_rows0, side 1 in groups of xf_rows1)
+  float* stat_partial = nullptr;
+  const float* xf_scale = nullptr;   // [2 * xf_G, K]
+  const float* xf_shift = nullptr;
+  long long xf_T0 = 0, xf_rows0 = 1, xf_rows1 = 1;
+  int xf_G = 1;
   // filled by the launcher
   int vec_f = 0, coalesced_rmw = 0, num_panels = 0, num_m_tiles = 0, cpp = 1;
   int dbg_flags = 0;

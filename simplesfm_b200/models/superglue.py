@@ -36,6 +36,28 @@ def arange_like(x, dim: int):
     return x.new_ones(x.shape[dim]).cumsum(0) - 1
 
 
+def attention(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor):
+    """ softmax(q^T k / sqrt(d)) v per head (superglue.py:85-89), reference layout: query (b, 64, 4, n),
+    key/value (b, 64, 4, m) CUDA f32 -> (out (b, 64, 4, n), prob (b, 4, n, m)).  This is the stand-alone fp32
+    form with the probabilities materialised; `SuperGlue.forward` uses the fused kernels instead. """
+    q = require_cuda(query, "query", torch.float32)
+    k = require_cuda(key, "key", torch.float32)
+    v = require_cuda(value, "value", torch.float32)
+    b, d, h, n = q.shape
+    m = k.shape[3]
+    if d != 64 or h != 4 or k.shape[:3] != (b, 64, 4) or v.shape != k.shape:
+        raise _lib.SfmError(-5, f"attention: expected (b,64,4,n)/(b,64,4,m) operands, got {tuple(q.shape)}, "
+                                f"{tuple(k.shape)}, {tuple(v.shape)}")
+    L = lib()
+    out = torch.empty_like(q)
+    prob = torch.empty(b, 4, n, m, dtype=torch.float32, device=q.device)
+    ws = torch.empty(max(L.sfm_attention_workspace_bytes(b, n, m), 256), dtype=torch.uint8, device=q.device)
+    with torch.cuda.device(q.device):
+        check(L.sfm_attention(ptr(q), ptr(k), ptr(v), b, n, m, ptr(out), ptr(prob), ptr(ws), ws.numel(),
+                              stream_ptr(q.device)))
+    return out, prob
+
+
 def log_optimal_transport(scores: torch.Tensor, alpha, iters: int) -> torch.Tensor:
     """ Perform Differentiable Optimal Transport in Log-space for stability (forward only).
     scores (b, m, n) CUDA f32 -> (b, m+1, n+1). """

@@ -196,6 +196,23 @@ def test_log_optimal_transport(dev):
     close(normalize_keypoints(t(g["nk_in"]).to(dev), (2, 1, 480, 640)), g["nk_out"], 1e-6, 1e-7)
 
 
+def test_attention_function(dev):
+    """Module-level `attention` (superglue.py:85-89) in the reference layout, prob materialised."""
+    from simplesfm_b200.models.superglue import attention
+    g = load_golden("sg_functions")
+    q, k, v = (t(g[n]).to(dev) for n in ("att_q", "att_k", "att_v"))
+    out, prob = attention(q, k, v)
+    close(out, g["att_out"], 1e-4, 1e-5)
+    ref_prob = torch.softmax(torch.einsum("bdhn,bdhm->bhnm", t(g["att_q"]), t(g["att_k"])) / 8.0, dim=-1)
+    close(prob, ref_prob.numpy(), 1e-4, 1e-6)
+    assert prob.shape == (2, 4, 33, 21)
+    # larger, tile-crossing shape against the oracle
+    gen = torch.Generator().manual_seed(5)
+    q, k, v = (torch.randn(3, 64, 4, n, generator=gen) for n in (301, 150, 150))
+    out, _ = attention(q.to(dev), k.to(dev), v.to(dev))
+    close(out, O.attention(q, k, v).numpy(), 1e-4, 1e-5)
+
+
 @pytest.mark.parametrize("mode", ["train", "eval"])
 def test_superglue_vs_oracle_ragged(sg, sg_weights, dev, mode):
     """Seeded inputs at a size the oracle finishes in seconds; K0 != K1, neither a multiple of 4."""
