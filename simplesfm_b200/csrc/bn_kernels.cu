@@ -170,13 +170,15 @@ __global__ void __launch_bounds__(256) bn_final_kernel(const float* __restrict__
   }
 }
 
-// Same result for partials whose blocks all hold exactly `rb` rows (what the GEMM epilogue writes): two
-// coalesced passes, no divisions in the loop.  CTA = (32 channels, group); lane = channel, warps stride blocks.
-__global__ void __launch_bounds__(256) bn_final_equal_kernel(const float* __restrict__ partial, int C, BnGroups gr,
-                                                             int nb0, int nb1, int rb, const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, float eps,
-                                                             float* __restrict__ scale, float* __restrict__ shift) {
-  __shared__ float red[8][32];
+// Same result for partials whose blocks all hold exactly `rb` rows (what the GEMM epilogue writes): one
+// coalesced pass, no divisions in the loop.  CTA = (32 channels, group); lane = channel, 32 warps stride the
+// blocks.  total M2 = sum M2_b + rb * (sum mean_b^2 - (sum mean_b)^2 / nb): only the (small) between-block term
+// is formed by subtraction.
+__global__ void __launch_bounds__(1024) bn_final_equal_kernel(const float* __restrict__ partial, int C, BnGroups gr,
+                                                              int nb0, int nb1, int rb, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps,
+                                                              float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ float red[3][32][33];
   const int g = blockIdx.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -184,27 +186,28 @@ __global__ void __launch_bounds__(256) bn_final_equal_kernel(const float* __rest
   const int nb = side ? nb1 : nb0;
   const long long b0 = side ? (long long)gr.G * nb0 + (long long)grp * nb1 : (long long)grp * nb0;
   const float2* src = reinterpret_cast<const float2*>(partial) + b0 * C + c;
-  float s = 0.f;
-  for (int b = w; b < nb; b += 8) s += src[(long long)b * C].x;
-  red[w][lane] = s;
-  __syncthreads();
-  float mean = 0.f;
-#pragma unroll
-  for (int k = 0; k < 8; k++) mean += red[k][lane];
-  mean /= (float)nb;
-  __syncthreads();
-  float q = 0.f;
-  for (int b = w; b < nb; b += 8) {
-    const float2 pm = src[(long long)b * C];
-    const float d = pm.x - mean;
-    q += fmaf(d * d, (float)rb, pm.y);
+  float s = 0.f, ss = 0.f, q = 0.f;
+#pragma unroll 4
+  for (int b = w; b < nb; b += 32) {
+    const float2 pm = __ldg(src + (long long)b * C);
+    s += pm.x;
+    ss = fmaf(pm.x, pm.x, ss);
+    q += pm.y;
   }
-  red[w][lane] = q;
+  red[0][w][lane] = s;
+  red[1][w][lane] = ss;
+  red[2][w][lane] = q;
   __syncthreads();
   if (w == 0) {
-    float m2 = 0.f;
+    s = ss = q = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; k++) m2 += red[k][lane];
+    for (int k = 0; k < 32; k++) {
+      s += red[0][k][lane];
+      ss += red[1][k][lane];
+      q += red[2][k][lane];
+    }
+    const float mean = s / (float)nb;
+    const float m2 = q + (float)rb * fmaxf(ss - s * mean, 0.f);
     const float var = m2 / ((float)nb * (float)rb);
     const float a = gamma[c] * (1.0f / sqrtf(var + eps));
     scale[g * C + c] = a;
@@ -301,7 +304,7 @@ int bn_finalize(const float* partial, int rb, int C, const BnGroups& g, const fl
   const int nb0 = (int)(g.T0 / g.G / rb), nb1 = (int)(g.T1 / g.G / rb);
   if (g.G * (nb0 + nb1) == 0) return SFM_OK;
   if (C % 32 == 0 && nb0 > 0 && nb1 > 0)
-    bn_final_equal_kernel<<<dim3(C / 32, 2 * g.G), 256, 0, st>>>(partial, C, g, nb0, nb1, rb, gamma, beta, eps, scale,
+    bn_final_equal_kernel<<<dim3(C / 32, 2 * g.G), 1024, 0, st>>>(partial, C, g, nb0, nb1, rb, gamma, beta, eps, scale,
                                                                   shift);
   else
     bn_final_kernel<<<dim3(cdiv(C, 8), 2 * g.G), 256, 0, st>>>(partial, C, g, nb0, nb1, rb, gamma, beta, eps, scale, shift);

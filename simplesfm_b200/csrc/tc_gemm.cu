@@ -131,6 +131,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
+    // One elected lane drives the ring.  Before loading a tile it asks the TMA unit to pull the NEXT tile's A
+    // boxes into L2, so the bytes in flight are not limited to the 64 KB smem ring.
     if (lane == 0) {
       int stage = 0, phase = 0, wphase = 0;
       for (int pj = slot; pj < n_pj; pj += n_slots) {
@@ -144,6 +146,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int kb = 0; kb < KBLOCKS; kb++) tma_load_2d(sW + kb * BN * 128, &mapW, &bars->w_full, kb * BK, wrow);
         for (int mt = sub; mt < p.num_m_tiles; mt += p.cpp) {
           const int arow = b * p.a_row_stride + mt * BM;
+          if ((p.l2_prefetch & 1) && mt + p.cpp < p.num_m_tiles) {
+            const int nrow = arow + p.cpp * BM;
+            for (int kb = 0; kb < KBLOCKS; kb++) {
+              if (kb < k1_blocks)
+                tma_prefetch_2d(&mapA, kb * BK, nrow);
+              else
+                tma_prefetch_2d(&mapA2, (kb - k1_blocks) * BK, nrow);
+            }
+          }
           for (int kb = 0; kb < KBLOCKS; kb++) {
             DBG_WAIT(0, mbar_wait(&bars->a_empty[stage], phase ^ 1));
             mbar_arrive_expect_tx(&bars->a_full[stage], A_STAGE_BYTES);
@@ -290,6 +301,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       named_bar_sync(1, 256);
       for (int mt = sub; mt < p.num_m_tiles; mt += p.cpp, tile++) {
         const int buf = tile & 1;
+        if ((p.l2_prefetch & 2) && p.accumulate_f && p.coalesced_rmw && mt + p.cpp < p.num_m_tiles && (wg_tid & 7) == 0) {
+          // pull the NEXT tile's fp32 residual rows into L2 (one 128-byte line per row and 32-column chunk): the
+          // read-modify-write below is latency-bound on these loads, and a prefetch holds no registers
+          const long long nrow0 = (long long)(mt + p.cpp) * BM + (wg_tid >> 3);
+#pragma unroll
+          for (int c = 0; c < HALF / 32; c++) {
+            const int n0 = panel * BN + wg * HALF + c * 32;
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+              const long long r = nrow0 + it * 16;
+              if (r < p.M) prefetch_l2(p.out_f + r * p.out_f_ld + n0);
+            }
+          }
+        }
         DBG_WAIT(0, mbar_wait(&bars->acc_full[buf], (tile >> 1) & 1));
         tc_fence_after();
         const int row = mt * BM + row_in_tile;  // row inside this batch
@@ -461,6 +486,7 @@ int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, co
   if (want_dbg && dbg == nullptr) cudaMalloc(&dbg, 148 * 3 * 6 * sizeof(long long));
   p.dbg = want_dbg ? dbg : nullptr;
   p.dbg_flags = getenv("SFM_TC_FLAGS") ? atoi(getenv("SFM_TC_FLAGS")) : 0;
+  p.l2_prefetch = getenv("SFM_TC_PREFETCH") ? atoi(getenv("SFM_TC_PREFETCH")) : 2;   // bit 0: A tiles, bit 1: residual
   if (want_dbg) cudaMemsetAsync(dbg, 0, 148 * 3 * 6 * sizeof(long long), st);
   tc_gemm_kernel<BN, KBLOCKS, XF><<<n_slots * cpp, XF ? GEMM_THREADS + 128 : GEMM_THREADS, smem, st>>>(mA, mA2, mW, mO, p);
   SFM_LAUNCH_CHECK();

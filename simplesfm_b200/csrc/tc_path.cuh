@@ -56,6 +56,7 @@ struct TcGemm {
   // filled by the launcher
   int vec_f = 0, coalesced_rmw = 0, num_panels = 0, num_m_tiles = 0, cpp = 1;
   int dbg_flags = 0;
+  int l2_prefetch = 2;   // bit 0: TMA-prefetch the next A tile into L2, bit 1: prefetch the next residual rows
   long long* dbg = nullptr;  // optional per-role wait-cycle counters (SFM_TC_DEBUG)
 };
 int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st);
