@@ -10,10 +10,16 @@
 
 namespace sfm {
 
+static bool sk_use_k16() {
+  static const bool on = getenv("SFM_SK_FP32") == nullptr;
+  return on;
+}
+
+
 namespace {
 
 struct SgBuffers {
-  float *X, *xk, *kin, *t0, *t1, *qkv, *msgp, *msg, *hid, *att, *bn_part, *bn_scale, *bn_shift, *md, *sk_fused, *sk_kb, *scores, *u, *v, *part, *max0, *max1;
+  float *X, *xk, *kin, *t0, *t1, *qkv, *msgp, *msg, *hid, *att, *bn_part, *bn_scale, *bn_shift, *md, *sk_fused, *sk_kb, *sk_k16f, *scores, *u, *v, *part, *max0, *max1;
   int *counters, *idx0, *idx1;
   int R, ldS;
 };
@@ -48,6 +54,8 @@ int carve(Arena& a, const SgCall& c, SgBuffers& b) {
   b.counters = a.get<int>(sinkhorn_counter_ints(c.B, c.K1));
   b.sk_fused = c.precision == 1 ? a.get<float>(sinkhorn_fused_floats(c.B, c.K0, c.K1)) : nullptr;
   b.sk_kb = c.precision == 1 ? a.get<float>((size_t)c.B * c.K0) : nullptr;
+  // fp16 copy of the scaling-form Sinkhorn matrix (bf16 precision mode): [B, K0, K1] halves
+  b.sk_k16f = (c.precision == 1 && sk_use_k16()) ? a.get<float>(((size_t)c.B * c.K0 * c.K1 + 1) / 2) : nullptr;
   b.max0 = a.get<float>((size_t)c.B * c.K0);
   b.max1 = a.get<float>((size_t)c.B * c.K1);
   b.idx0 = a.get<int>((size_t)c.B * c.K0);
@@ -235,6 +243,7 @@ int sg_forward(sfm_ctx* h, const SgCall& c, void* ws, size_t ws_bytes, bool dry,
   s.fast = c.precision == 1;
   s.fused_part = b.sk_fused;
   s.kb = b.sk_kb;
+  s.k16 = reinterpret_cast<__half*>(b.sk_k16f);
   ProfScope ps(h, SFM_PROF_SINKHORN, st);
   SFM_TRY(sinkhorn_run(s, st));
   return sinkhorn_match(s, c.thr, b.max0, b.idx0, b.max1, b.idx1, c.m0, c.m1, c.ms0, c.ms1, st);

@@ -1,4 +1,5 @@
 #include "sg_kernels.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace sfm {
@@ -307,8 +308,12 @@ __global__ void __launch_bounds__(256) sk_col_kernel(const float* __restrict__ S
 constexpr int FUSED_RB = 64;
 
 // prologue: c_i = max_j S_ij ; S_ij <- exp(S_ij - c_i) in place ; kb_i = exp(alpha - c_i).  Warp per row.
+// With k16 != nullptr the iterations run on a half-precision copy K16_ij = fp16(2^14 K_ij) (half the HBM bytes
+// per sweep; the 2^14 keeps entries down to e^-19 of the row maximum in fp16's normal range, 11-bit mantissa);
+// the final arg-max passes still read the fp32 K.
+constexpr float K16_SCALE = 16384.f, K16_INV = 1.f / 16384.f;
 __global__ void __launch_bounds__(256) sks_prologue_kernel(float* __restrict__ S, int N, int M, float alpha,
-                                                           float* __restrict__ kb) {
+                                                           float* __restrict__ kb, __half* __restrict__ k16) {
   const int b = blockIdx.y;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -317,22 +322,37 @@ __global__ void __launch_bounds__(256) sks_prologue_kernel(float* __restrict__ S
   float m = -INFINITY;
   for (int j = lane; j < M; j += 32) m = fmaxf(m, sr[j]);
   m = warp_max(m);
-  for (int j = lane; j < M; j += 32) sr[j] = __expf(sr[j] - m);
+  if (k16 != nullptr) {
+    __half* hr = k16 + ((long long)b * N + row) * M;
+    for (int j = lane * 2; j < M; j += 64) {   // M % 4 == 0
+      const float2 sv = *reinterpret_cast<const float2*>(sr + j);
+      const float e0 = __expf(sv.x - m), e1 = __expf(sv.y - m);
+      *reinterpret_cast<float2*>(sr + j) = make_float2(e0, e1);
+      *reinterpret_cast<__half2*>(hr + j) = __floats2half2_rn(e0 * K16_SCALE, e1 * K16_SCALE);
+    }
+  } else {
+    for (int j = lane; j < M; j += 32) sr[j] = __expf(sr[j] - m);
+  }
   if (lane == 0) kb[(long long)b * N + row] = __expf(alpha - m);
 }
 
 // fused sweep: A for the rows of this block, then the block's column sums of K_ij A_i
-template <int G>
-__global__ void __launch_bounds__(256) sks_fused_kernel(const float* __restrict__ K, int N, int M, float ealpha,
+template <int G, bool H16>
+__global__ void __launch_bounds__(256, 2) sks_fused_kernel(const void* __restrict__ Kp, int N, int M, float ealpha,
                                                         const float* __restrict__ kb, const float* __restrict__ Bv,
                                                         float* __restrict__ Av, float* __restrict__ part, float mu,
                                                         float mu_bin) {
-  constexpr int RS = 16 / G;
+  // rows per step: the fp16 matrix is kept PACKED in registers (converted once for the row sums and once for
+  // the column sums), so twice as many rows are in flight for the same register budget -- the sweep is bound
+  // by bytes in flight per SM, not by arithmetic
+  constexpr int RS = (H16 ? 32 : 16) / G;
+  constexpr int XW = H16 ? 2 : 4;   // registers per 4 matrix elements
   __shared__ float red[2][8][RS];
   __shared__ float red_bin[8];
   const int b = blockIdx.y, blk = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* Kb_ = K + (long long)b * N * M;
+  const float* Kb_ = reinterpret_cast<const float*>(Kp) + (long long)b * N * M;          // !H16
+  const __half* Kh_ = reinterpret_cast<const __half*>(Kp) + (long long)b * N * M;        // H16
   const float* Bb = Bv + (long long)b * (M + 1);
   float* Ab = Av + (long long)b * (N + 1);
   const float* kbb = kb + (long long)b * N;
@@ -363,60 +383,81 @@ __global__ void __launch_bounds__(256) sks_fused_kernel(const float* __restrict_
   for (int c = 0; c < 4 * G; c++) cs[c] = 0.f;
   const int row0 = blk * FUSED_RB;
   int par = 0;
+  auto unpack = [](const uint32_t* xr, float* f) {   // 4 matrix elements of one (row, g) slot
+    if (H16) {
+      // volatile: the two uses of a slot (row sums, column sums) must each re-convert from the packed
+      // registers instead of keeping 4x as many floats live across the barrier
+      asm volatile("{.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;}"
+                   : "=f"(f[0]), "=f"(f[1]) : "r"(xr[0]));
+      asm volatile("{.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;}"
+                   : "=f"(f[2]), "=f"(f[3]) : "r"(xr[1]));
+    } else {
+      f[0] = __uint_as_float(xr[0]); f[1] = __uint_as_float(xr[1]);
+      f[2] = __uint_as_float(xr[2]); f[3] = __uint_as_float(xr[3]);
+    }
+  };
   for (int step = 0; step < FUSED_RB / RS; step++, par ^= 1) {
     const int i0 = row0 + step * RS;
     if (i0 >= N) break;   // block-uniform
-    float x[RS][4 * G];
+    uint32_t x[RS][G][XW];
 #pragma unroll
     for (int r = 0; r < RS; r++) {
       const bool rok = i0 + r < N;
-      const float* sr = Kb_ + (long long)(i0 + r) * M;
 #pragma unroll
       for (int g = 0; g < G; g++) {
         const int col = (g * 256 + tid) * 4;
-        float4 t = (rok && col < M) ? *reinterpret_cast<const float4*>(sr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-        x[r][4 * g] = t.x; x[r][4 * g + 1] = t.y; x[r][4 * g + 2] = t.z; x[r][4 * g + 3] = t.w;
+        if (H16) {
+          const uint2 t = (rok && col < M) ? *reinterpret_cast<const uint2*>(Kh_ + (long long)(i0 + r) * M + col)
+                                           : make_uint2(0u, 0u);
+          x[r][g][0] = t.x; x[r][g][1] = t.y;
+        } else {
+          const uint4 t = (rok && col < M) ? *reinterpret_cast<const uint4*>(Kb_ + (long long)(i0 + r) * M + col)
+                                           : make_uint4(0u, 0u, 0u, 0u);
+          x[r][g][0] = t.x; x[r][g][1] = t.y; x[r][g][XW - 2] = t.z; x[r][g][XW - 1] = t.w;
+        }
       }
     }
-    float rsum[RS];
 #pragma unroll
     for (int r = 0; r < RS; r++) {
       float sacc = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4 * G; c++) sacc = fmaf(x[r][c], bj[c], sacc);
-      rsum[r] = warp_sum(sacc);
-    }
-    if (lane == 0) {
+      for (int g = 0; g < G; g++) {
+        float f[4];
+        unpack(x[r][g], f);
 #pragma unroll
-      for (int r = 0; r < RS; r++) red[par][warp][r] = rsum[r];
+        for (int e = 0; e < 4; e++) sacc = fmaf(f[e], bj[4 * g + e], sacc);
+      }
+      sacc = warp_sum(sacc);
+      if (lane == 0) red[par][warp][r] = sacc;
     }
     __syncthreads();
-    float ai[RS];
 #pragma unroll
-    for (int r = 0; r < RS; r++) {
+    for (int r = 0; r < RS; r++) {   // one scaling factor live at a time: keeps the step inside 128 registers
       float tot = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; w++) tot += red[par][w][r];
+      if (H16) tot *= K16_INV;
       const bool rok = i0 + r < N;
       const float kbr = rok ? kbb[i0 + r] : 1.f;
-      ai[r] = rok ? mu / fmaf(kbr, bbin, tot) : 0.f;
+      const float ai = rok ? mu / fmaf(kbr, bbin, tot) : 0.f;
+      if (tid == r && rok) Ab[i0 + r] = ai;
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        float f[4];
+        unpack(x[r][g], f);
+#pragma unroll
+        for (int e = 0; e < 4; e++) cs[4 * g + e] = fmaf(f[e], ai, cs[4 * g + e]);
+      }
     }
-    if (warp == 0 && lane < RS && i0 + lane < N) {
-      float val = ai[0];
-#pragma unroll
-      for (int r = 1; r < RS; r++) val = lane == r ? ai[r] : val;
-      Ab[i0 + lane] = val;
-    }
-#pragma unroll
-    for (int c = 0; c < 4 * G; c++)
-#pragma unroll
-      for (int r = 0; r < RS; r++) cs[c] = fmaf(x[r][c], ai[r], cs[c]);
   }
   float* pb = part + ((long long)b * gridDim.x + blk) * M;
 #pragma unroll
   for (int g = 0; g < G; g++) {
     const int col = (g * 256 + tid) * 4;
-    if (col < M) *reinterpret_cast<float4*>(pb + col) = make_float4(cs[4 * g], cs[4 * g + 1], cs[4 * g + 2], cs[4 * g + 3]);
+    const float sc = H16 ? K16_INV : 1.f;
+    if (col < M)
+      *reinterpret_cast<float4*>(pb + col) =
+          make_float4(cs[4 * g] * sc, cs[4 * g + 1] * sc, cs[4 * g + 2] * sc, cs[4 * g + 3] * sc);
   }
 }
 
@@ -790,17 +831,22 @@ int sinkhorn_run(const SinkhornArgs& a, cudaStream_t st) {
     const float ealpha = expf(a.alpha);
     const float mu = 1.0f / ((float)N + (float)M), mu_bin = (float)M * mu, nu_bin = (float)N * mu;
     float* K = const_cast<float*>(a.S);   // the score matrix is overwritten by K = exp(S - rowmax)
-    sks_prologue_kernel<<<dim3(cdiv(N, 8), B), 256, 0, st>>>(K, N, M, a.alpha, a.kb);
+    sks_prologue_kernel<<<dim3(cdiv(N, 8), B), 256, 0, st>>>(K, N, M, a.alpha, a.kb, a.k16);
     fill_kernel<<<cdiv(nv, 256), 256, 0, st>>>(a.v, nv, 1.f);   // B = exp(v) = 1
     dim3 fgrid(nblk, B);
     dim3 cg(cdiv(M, 256) + 1, B);
+    const bool h16 = a.k16 != nullptr;
+    const void* Kit = h16 ? (const void*)a.k16 : (const void*)K;
     for (int it = 0; it < a.iters; it++) {
-      if (M <= 1024)
-        sks_fused_kernel<1><<<fgrid, 256, 0, st>>>(K, N, M, ealpha, a.kb, a.v, a.u, a.fused_part, mu, mu_bin);
-      else if (M <= 2048)
-        sks_fused_kernel<2><<<fgrid, 256, 0, st>>>(K, N, M, ealpha, a.kb, a.v, a.u, a.fused_part, mu, mu_bin);
-      else
-        sks_fused_kernel<4><<<fgrid, 256, 0, st>>>(K, N, M, ealpha, a.kb, a.v, a.u, a.fused_part, mu, mu_bin);
+#define SKS_LAUNCH(G, H) sks_fused_kernel<G, H><<<fgrid, 256, 0, st>>>(Kit, N, M, ealpha, a.kb, a.v, a.u, a.fused_part, mu, mu_bin)
+      if (M <= 1024) {
+        if (h16) SKS_LAUNCH(1, true); else SKS_LAUNCH(1, false);
+      } else if (M <= 2048) {
+        if (h16) SKS_LAUNCH(2, true); else SKS_LAUNCH(2, false);
+      } else {
+        if (h16) SKS_LAUNCH(4, true); else SKS_LAUNCH(4, false);
+      }
+#undef SKS_LAUNCH
       sks_combine_kernel<<<cg, 256, 0, st>>>(a.fused_part, nblk, N, M, ealpha, a.kb, a.u, a.v, mu, nu_bin);
     }
     count_launches(2 + 2 * a.iters);

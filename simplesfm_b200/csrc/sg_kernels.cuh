@@ -1,5 +1,6 @@
 // SuperGlue element-wise / reduction kernels shared by the fp32 and bf16 paths.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace sfm {
@@ -35,6 +36,7 @@ struct SinkhornArgs {
   int R;            // row splits of the column pass
   float* fused_part = nullptr;  // [B, ceil(N/64), M] column partial sums of the fused single-read sweep
   float* kb = nullptr;          // [B, N] dustbin-column factors exp(alpha - rowmax) of the scaling form
+  __half* k16 = nullptr;        // optional [B, N, M] fp16 copy of the scaling-form matrix the iterations stream
   int sub_batch = 0;  // pairs per L2-resident sweep group (0 = auto)
   bool fast = false;  // ex2.approx exponentials (bf16 precision mode) instead of IEEE expf
 };
