@@ -75,7 +75,9 @@ __device__ __forceinline__ uint32_t bn_relu_pair(uint32_t x, float a0, float b0,
 // XF = true adds four "transform" warps that apply the train-mode BatchNorm affine + ReLU
 // (superglue.py:56-58) to every A stage in shared memory between the TMA landing and the MMA, so the
 // normalised hidden activations never make a round trip through HBM.
-template <int BN, int KBLOCKS, bool XF>
+// RMW = true compiles the epilogue for the coalesced residual update only (out_f += result), which keeps its
+// prefetched fp32 values in registers across tiles.
+template <int BN, int KBLOCKS, bool XF, bool RMW>
 __global__ void __launch_bounds__(XF ? GEMM_THREADS + 128 : GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO, TcGemm p) {
@@ -290,6 +292,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int row_in_tile = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     int tile = 0;
+    [[maybe_unused]] float4 oldb[RMW ? 2 : 1][RMW ? 8 : 1];  // fp32 master values of the chunk being updated / the next one
+    [[maybe_unused]] bool have_old = false;                   // oldb[0] already holds chunk 0 of the coming tile
     for (int pj = slot; pj < n_pj; pj += n_slots) {
       const int b = pj / p.num_panels, panel = pj % p.num_panels;
       // stage this panel's bias (both warpgroups take part; 256 threads)
@@ -301,20 +305,88 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       named_bar_sync(1, 256);
       for (int mt = sub; mt < p.num_m_tiles; mt += p.cpp, tile++) {
         const int buf = tile & 1;
-        if ((p.l2_prefetch & 2) && p.accumulate_f && p.coalesced_rmw && mt + p.cpp < p.num_m_tiles && (wg_tid & 7) == 0) {
-          // pull the NEXT tile's fp32 residual rows into L2 (one 128-byte line per row and 32-column chunk): the
-          // read-modify-write below is latency-bound on these loads, and a prefetch holds no registers
-          const long long nrow0 = (long long)(mt + p.cpp) * BM + (wg_tid >> 3);
-#pragma unroll
-          for (int c = 0; c < HALF / 32; c++) {
-            const int n0 = panel * BN + wg * HALF + c * 32;
+        if constexpr (RMW) {
+          // ---- residual update X += delta (fp32 master + bf16 shadow).  The accumulator chunk goes through a
+          // fp32 slab so that the global read-modify-write is full-line coalesced (4 rows x 128 B per warp op),
+          // and the fp32 values to be updated are loaded one chunk AHEAD (the first chunk of a tile while the
+          // previous tile is still being written / the MMA is still running): the path is bound by HBM
+          // latency x bytes in flight, not by arithmetic.
+          constexpr int NCH = HALF / 32;
+          const int rsub = wg_tid >> 3, ch = wg_tid & 7;
+          auto load_old = [&](int mt_, int c_, float4* dst) {
+            const long long g0 = (long long)mt_ * BM;
+            const float* src = p.out_f + panel * BN + wg * HALF + c_ * 32 + ch * 4;
 #pragma unroll
             for (int it = 0; it < 8; it++) {
-              const long long r = nrow0 + it * 16;
-              if (r < p.M) prefetch_l2(p.out_f + r * p.out_f_ld + n0);
+              const long long r = g0 + it * 16 + rsub;
+              dst[it] = r < p.M ? *reinterpret_cast<const float4*>(src + r * p.out_f_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          };
+          if ((p.l2_prefetch & 2) && mt + p.cpp < p.num_m_tiles && ch == 0) {
+            // and the tile after that is pulled into L2 (a prefetch holds no registers)
+            const long long nrow0 = (long long)(mt + p.cpp) * BM + rsub;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+              const int n0 = panel * BN + wg * HALF + c * 32;
+#pragma unroll
+              for (int it = 0; it < 8; it++) {
+                const long long r = nrow0 + it * 16;
+                if (r < p.M) prefetch_l2(p.out_f + r * p.out_f_ld + n0);
+              }
             }
           }
-        }
+          if (!have_old) load_old(mt, 0, oldb[0]);
+          DBG_WAIT(0, mbar_wait(&bars->acc_full[buf], (tile >> 1) & 1));
+          tc_fence_after();
+          const uint32_t tcol0 = lane_addr + buf * BN + wg * HALF;
+          const long long grow0 = (long long)mt * BM;
+#pragma unroll
+          for (int c = 0; c < NCH; c++) {
+            const int cl = wg * HALF + c * 32;
+            const int n0 = panel * BN + cl;
+            uint32_t r[32];
+            tmem_ld_32x32(tcol0 + c * 32, r);
+            tmem_wait_ld();
+            named_bar_sync(2 + wg, 128);  // previous chunk's readers are done with the slab
+            const uint32_t rowa = slab_u32 + row_in_tile * 128;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              float x[4];
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                x[e] = fmaf(__uint_as_float(r[4 * j + e]), p.alpha, sBias[cl + 4 * j + e]);
+                if (p.relu) x[e] = fmaxf(x[e], 0.f);
+              }
+              sts128(rowa + ((j ^ (row_in_tile & 7)) << 4), __float_as_uint(x[0]), __float_as_uint(x[1]),
+                     __float_as_uint(x[2]), __float_as_uint(x[3]));
+            }
+            named_bar_sync(2 + wg, 128);
+            if (c + 1 < NCH) {
+              load_old(mt, c + 1, oldb[(c + 1) & 1]);
+            } else if (mt + p.cpp < p.num_m_tiles) {
+              load_old(mt + p.cpp, 0, oldb[0]);
+              have_old = true;
+            } else {
+              have_old = false;
+            }
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+              const int rr = it * 16 + rsub;
+              const float4 d = lds128(slab_u32 + rr * 128 + ((ch ^ (rr & 7)) << 4));
+              const float4 od = oldb[c & 1][it];
+              const float4 o = make_float4(od.x + d.x, od.y + d.y, od.z + d.z, od.w + d.w);
+              if (grow0 + rr < p.M) {
+                *reinterpret_cast<float4*>(p.out_f + (grow0 + rr) * p.out_f_ld + n0 + ch * 4) = o;
+                if (p.out_h != nullptr)
+                  *reinterpret_cast<uint2*>(p.out_h + (grow0 + rr) * p.out_h_ld + n0 + ch * 4) =
+                      make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+        } else {
         DBG_WAIT(0, mbar_wait(&bars->acc_full[buf], (tile >> 1) & 1));
         tc_fence_after();
         const int row = mt * BM + row_in_tile;  // row inside this batch
@@ -336,40 +408,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             float x = fmaf(__uint_as_float(r[c & 1][j]), p.alpha, sBias[cl + j]);
             if (p.relu) x = fmaxf(x, 0.f);
             v[j] = x;
-          }
-          if (p.accumulate_f && p.coalesced_rmw) {
-            // residual update X += delta through a fp32 slab so that the global read-modify-write of the
-            // fp32 master and the bf16 shadow store are full-line coalesced (4 rows x 128 B per warp op)
-            named_bar_sync(2 + wg, 128);  // previous chunk's readers are done with the slab
-            const uint32_t rowa = slab_u32 + row_in_tile * 128;
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-              sts128(rowa + ((j ^ (row_in_tile & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-                     __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-            named_bar_sync(2 + wg, 128);
-            const int rsub = wg_tid >> 3, ch = wg_tid & 7;
-            float4 old[8];
-            const long long grow0 = (long long)mt * BM;
-#pragma unroll
-            for (int it = 0; it < 8; it++) {
-              const int r = it * 16 + rsub;
-              old[it] = (grow0 + r < p.M)
-                            ? *reinterpret_cast<const float4*>(p.out_f + (grow0 + r) * p.out_f_ld + n0 + ch * 4)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int it = 0; it < 8; it++) {
-              const int r = it * 16 + rsub;
-              const float4 d = lds128(slab_u32 + r * 128 + ((ch ^ (r & 7)) << 4));
-              float4 o = make_float4(old[it].x + d.x, old[it].y + d.y, old[it].z + d.z, old[it].w + d.w);
-              if (grow0 + r < p.M) {
-                *reinterpret_cast<float4*>(p.out_f + (grow0 + r) * p.out_f_ld + n0 + ch * 4) = o;
-                if (p.out_h != nullptr)
-                  *reinterpret_cast<uint2*>(p.out_h + (grow0 + r) * p.out_h_ld + n0 + ch * 4) =
-                      make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
-              }
-            }
-            continue;
           }
           if (of != nullptr && row_ok && n0 < p.N) {
             const bool full = n0 + 32 <= p.N;
@@ -448,9 +486,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+        }  // !RMW
       }
     }
-    if (p.out_h != nullptr && wg_tid == 0) tma_store_wait_all();
+    if (!RMW && p.out_h != nullptr && wg_tid == 0) tma_store_wait_all();
   }
   if (p.dbg != nullptr && lane == 0 && (warp <= 2)) {
     long long* d = p.dbg + ((long long)blockIdx.x * 3 + warp) * 6;
@@ -461,7 +500,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-template <int BN, int KBLOCKS, bool XF = false>
+template <int BN, int KBLOCKS, bool XF = false, bool RMW = false>
 int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mW,
            const CUtensorMap& mO, int num_sms, cudaStream_t st) {
   TcGemm p = p_in;
@@ -478,7 +517,7 @@ int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, co
                       sizeof(Barriers) + 1024;
   static bool configured = false;
   if (!configured) {
-    SFM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, KBLOCKS, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SFM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, KBLOCKS, XF, RMW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   static long long* dbg = nullptr;
@@ -488,7 +527,7 @@ int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, co
   p.dbg_flags = getenv("SFM_TC_FLAGS") ? atoi(getenv("SFM_TC_FLAGS")) : 0;
   p.l2_prefetch = getenv("SFM_TC_PREFETCH") ? atoi(getenv("SFM_TC_PREFETCH")) : 2;   // bit 0: A tiles, bit 1: residual
   if (want_dbg) cudaMemsetAsync(dbg, 0, 148 * 3 * 6 * sizeof(long long), st);
-  tc_gemm_kernel<BN, KBLOCKS, XF><<<n_slots * cpp, XF ? GEMM_THREADS + 128 : GEMM_THREADS, smem, st>>>(mA, mA2, mW, mO, p);
+  tc_gemm_kernel<BN, KBLOCKS, XF, RMW><<<n_slots * cpp, XF ? GEMM_THREADS + 128 : GEMM_THREADS, smem, st>>>(mA, mA2, mW, mO, p);
   SFM_LAUNCH_CHECK();
   if (want_dbg) {
     static long long host[148 * 3 * 6];
@@ -576,16 +615,22 @@ int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
             ((reinterpret_cast<uintptr_t>(p.out_f) & 15) == 0);
   q.coalesced_rmw = p.accumulate_f && q.vec_f && p.batch == 1 && (p.N % 32 == 0) &&
                     (p.out_h == nullptr || p.out_h_ld % 4 == 0);
+  const bool rmw = q.coalesced_rmw != 0;
+  SFM_REQUIRE(p.xf_scale == nullptr || rmw, "tc_gemm: fused BatchNorm apply is only built for the residual-update epilogue");
   if (p.K == 128) {
+    q.coalesced_rmw = 0;   // K = 128 shapes never carry the residual stream: generic epilogue
     if (wide) return launch<256, 2>(q, mA, mA2, mW, mO, num_sms, st);
     return launch<128, 2>(q, mA, mA2, mW, mO, num_sms, st);
   }
   if (p.K == 256) {
-    if (wide) return launch<256, 4>(q, mA, mA2, mW, mO, num_sms, st);
-    return launch<128, 4>(q, mA, mA2, mW, mO, num_sms, st);
+    if (wide) return rmw ? launch<256, 4, false, true>(q, mA, mA2, mW, mO, num_sms, st)
+                         : launch<256, 4>(q, mA, mA2, mW, mO, num_sms, st);
+    return rmw ? launch<128, 4, false, true>(q, mA, mA2, mW, mO, num_sms, st)
+               : launch<128, 4>(q, mA, mA2, mW, mO, num_sms, st);
   }
-  if (p.xf_scale != nullptr) return launch<128, 8, true>(q, mA, mA2, mW, mO, num_sms, st);
-  return launch<128, 8>(q, mA, mA2, mW, mO, num_sms, st);
+  if (p.xf_scale != nullptr) return launch<128, 8, true, true>(q, mA, mA2, mW, mO, num_sms, st);
+  return rmw ? launch<128, 8, false, true>(q, mA, mA2, mW, mO, num_sms, st)
+             : launch<128, 8>(q, mA, mA2, mW, mO, num_sms, st);
 }
 
 }  // namespace tc
