@@ -104,6 +104,10 @@ SFM_API int sfm_superpoint_describe(sfm_handle_t h, int n_img, int H, int W, int
 SFM_API int sfm_superpoint_tap(int n_img, int H, int W, int precision, int which, void* workspace, size_t workspace_bytes,
                        float** out_ptr, size_t* out_floats);
 
+/* image ingestion (matcher.py:360-367: `np.array(Image.open(..).convert('L')).astype('float32') / 255`): the
+ * 8-bit grey pixels are uploaded as they are and converted on the device, bit-identically (IEEE division) */
+SFM_API int sfm_u8_to_unit_f32(const uint8_t* pixels, float* out, size_t n, void* stream);
+
 /* module-level functions of superpoint.py */
 SFM_API int sfm_simple_nms(const float* scores, float* out, int n_img, int H, int W, int nms_radius, void* stream); /* :9-24 */
 SFM_API int sfm_sample_descriptors(const float* dmap_nhwc, int n_img, int h, int w, const float* kpts_xy, const int* counts,

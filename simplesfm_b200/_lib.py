@@ -55,6 +55,7 @@ _SIGNATURES = {
                                         C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfm_superglue_tap": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "sfm_u8_to_unit_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfm_attention_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "sfm_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -349,6 +349,11 @@ int sfm_superpoint_tap(int n_img, int H, int W, int precision, int which, void* 
   return sp_tap(n_img, H, W, precision, which, ws, ws_bytes, out_ptr, out_floats);
 }
 
+int sfm_u8_to_unit_f32(const uint8_t* pixels, float* out, size_t n, void* stream) {
+  SFM_REQUIRE(n == 0 || (pixels && out), "sfm_u8_to_unit_f32: NULL argument");
+  return sp_u8_to_unit_f32(pixels, out, (long long)n, (cudaStream_t)stream);
+}
+
 int sfm_simple_nms(const float* scores, float* out, int n_img, int H, int W, int nms_radius, void* stream) {
   SFM_REQUIRE(scores && out, "sfm_simple_nms: NULL argument");
   return sp_nms(scores, out, n_img, H, W, nms_radius, (cudaStream_t)stream);

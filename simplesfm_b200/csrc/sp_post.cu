@@ -419,4 +419,38 @@ int sp_sample_descriptors(const float* dmap, int n_img, int h, int w, const floa
   return SFM_OK;
 }
 
+// ---- image ingestion: 8-bit grey -> float in [0,1], exactly numpy's `astype(float32) / 255`
+// (matcher.py:360: IEEE single-precision division), 16 pixels per thread
+namespace {
+__global__ void u8_to_unit_kernel(const uint4* __restrict__ in16, const unsigned char* __restrict__ in,
+                                  float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long base = i * 16;
+  if (base >= n) return;
+  if (in16 != nullptr && base + 16 <= n) {
+    const uint4 v = in16[i];
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float4 o;
+      o.x = __fdiv_rn((float)(w[k] & 0xffu), 255.f);
+      o.y = __fdiv_rn((float)((w[k] >> 8) & 0xffu), 255.f);
+      o.z = __fdiv_rn((float)((w[k] >> 16) & 0xffu), 255.f);
+      o.w = __fdiv_rn((float)(w[k] >> 24), 255.f);
+      *reinterpret_cast<float4*>(out + base + 4 * k) = o;
+    }
+  } else {
+    for (long long j = base; j < n && j < base + 16; j++) out[j] = __fdiv_rn((float)in[j], 255.f);
+  }
+}
+}  // namespace
+
+int sp_u8_to_unit_f32(const unsigned char* in, float* out, long long n, cudaStream_t st) {
+  if (n == 0) return SFM_OK;
+  const bool vec = (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  u8_to_unit_kernel<<<cdiv(cdiv(n, 16), 256), 256, 0, st>>>(vec ? reinterpret_cast<const uint4*>(in) : nullptr, in, out, n);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
 }  // namespace sfm

@@ -14,4 +14,7 @@ int sp_rank_sort(const int* cand_pix, const float* cand_score, const int* counts
 int sp_sample_descriptors(const float* dmap, int n_img, int h, int w, const float* kpts_xy, const int* counts,
                           int kp_cap, int align_corners, float* out, int ld_out, cudaStream_t st);
 
+// 8-bit grey image -> float32 / 255 (bit-identical to the reference's host conversion, matcher.py:360)
+int sp_u8_to_unit_f32(const unsigned char* in, float* out, long long n, cudaStream_t st);
+
 }  // namespace sfm

@@ -77,7 +77,9 @@ class Matcher(object):
                  device: str = 'cuda',
                  shard_pairs: bool = True,
                  fuse_chunks: int = 16,
-                 superpoint_precision: str = 'fp32'):
+                 superpoint_precision: str = 'fp32',
+                 extract_batch: int = 8,
+                 decode_threads: int = 4):
 
         self.matcher_type = matcher_type
         self.device = torch.device(device)
@@ -92,6 +94,10 @@ class Matcher(object):
                                                 max_keypoints=max_keypoints,
                                                 device=device, precision=superpoint_precision)
         self.super_point_extractor.cuda()
+        # image ingestion: images are decoded ahead on `decode_threads` threads, uploaded as 8-bit pixels and run
+        # through SuperPoint `extract_batch` at a time (1 = the reference's one-image loop); see ingest.py
+        self.extract_batch = max(1, int(extract_batch))
+        self.decode_threads = max(1, int(decode_threads))
 
         if self.matcher_type == 'simple':
             self.matcher = SimpleMatcher(match_threshold)
@@ -250,6 +256,12 @@ class Matcher(object):
             data['mask'] = mask
         return self.super_point_extractor(data)
 
+    def _extract_stream(self, items) -> List[Frame]:
+        """Frames for an iterable of (grey image (H,W) u8 | f32, mask | None) host arrays, in order."""
+        from ..ingest import FrameExtractor
+        ex = FrameExtractor(self.super_point_extractor, self.extract_batch)
+        return [Frame(e.descriptors, e.keypoints, e.scores, e.image) for e in ex.extract(items)]
+
     def match_datasets(self,
                        datasets,
                        match_pairs_filter: callable = None,
@@ -277,6 +289,21 @@ class Matcher(object):
             datasets = [datasets]
 
         dataset_split_bd_index = []
+        if self.extract_batch > 1:
+            def stream():
+                nonlocal image_bd_index
+                for dataset in datasets:
+                    for data in DataLoader(dataset, batch_size=1, shuffle=False):
+                        images_names = '_'.join(data['path_rgb'][0].split('/')[-image_name_path_shift:])
+                        images_bd_index_names[image_bd_index] = images_names
+                        image_bd_index += 1
+                        img = data['rgb'][0, 0].numpy().astype(np.float32, copy=False)
+                        msk = (data['mask'][0, 0].numpy() > 0) if 'mask' in data else None
+                        yield img, msk
+                    dataset_split_bd_index.append(image_bd_index)
+            processed_frames = self._extract_stream(stream())
+            num_keypoints = sum(len(f.keypoints_poses) for f in processed_frames)
+            datasets = []
         for dataset in datasets:
             image_dataloader = DataLoader(dataset, batch_size=1, shuffle=False)
             for data in image_dataloader:
@@ -317,7 +344,23 @@ class Matcher(object):
         images_bd_index_names = {}
         processed_frames = []
         num_keypoints = 0
-        while True:
+        if self.extract_batch > 1:
+            def stream():
+                nonlocal image_bd_index
+                while True:
+                    image, status, img_path = vs.next_frame()
+                    image_mask = None
+                    if vs_mask is not None:
+                        image_mask, status_mask, img_mask_path = vs_mask.next_frame()
+                        status &= status_mask
+                    if status is False:
+                        return
+                    images_bd_index_names[image_bd_index] = img_path.split('/')[-1]
+                    image_bd_index += 1
+                    yield np.asarray(image, dtype=np.float32), (None if image_mask is None else image_mask > 0)
+            processed_frames = self._extract_stream(stream())
+            num_keypoints = sum(len(f.keypoints_poses) for f in processed_frames)
+        while self.extract_batch <= 1:
             image, status, img_path = vs.next_frame()
             if vs_mask is not None:
                 image_mask, status_mask, img_mask_path = vs_mask.next_frame()
@@ -368,6 +411,24 @@ class Matcher(object):
         with open(views_data_json_path, encoding="UTF-8") as file:
             views_data = json.load(file)
 
+        if self.extract_batch > 1:
+            from ..ingest import decode_ahead, load_grey_u8
+
+            def loader(item):
+                def load():
+                    img = load_grey_u8(Path(dataset_path, item['file_path']))
+                    msk = load_grey_u8(Path(dataset_path, item[dataset_mask_name])) if dataset_mask_name is not None else None
+                    return img, msk          # mask: nonzero grey level == `image_mask / 255 > 0`
+                return load
+
+            frames_meta = views_data['frames']
+            processed_frames = self._extract_stream(decode_ahead([loader(it) for it in frames_meta],
+                                                                 self.decode_threads))
+            for item in frames_meta:
+                images_bd_index_names[image_bd_index] = item['file_path'].split('/')[-1]
+                image_bd_index += 1
+            num_keypoints = sum(len(f.keypoints_poses) for f in processed_frames)
+            views_data = {'frames': []}
         for item in views_data['frames']:
             image = np.array(Image.open(Path(dataset_path, item['file_path'])).convert('L')).astype('float32') / 255
             image_name = item['file_path'].split('/')[-1]

@@ -1,0 +1,127 @@
+"""Image ingestion: the three image sources of `Matcher` (matcher.py:167-400) through the
+batched pipeline (threaded decode, 8-bit upload, device-side /255, batched SuperPoint) must give exactly what
+the reference's one-image-at-a-time loop gives."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import t  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _grey_u8(seed, H=240, W=320, shift=(0, 0)):
+    from simplesfm_b200 import synthetic
+    im = synthetic.textured_image(seed, H, W, shift=shift)[0, 0].numpy()
+    return np.clip(np.rint(im * 255), 0, 255).astype(np.uint8)
+
+
+def _same_frames(fa, fb):
+    assert len(fa) == len(fb)
+    for a, b in zip(fa, fb):
+        assert torch.equal(a.keypoints_poses, b.keypoints_poses)
+        assert torch.equal(a.scores, b.scores)
+        assert torch.equal(a.descriptors, b.descriptors)
+        assert a.image.shape == b.image.shape and torch.equal(a.image, b.image)
+
+
+def _same_tables(ta, tb):
+    assert set(ta) == set(tb)
+    for k in ta:
+        assert np.array_equal(ta[k], tb[k]), k
+
+
+def test_u8_to_unit_f32_matches_numpy(dev):
+    from simplesfm_b200._lib import check, lib, ptr, stream_ptr
+    for n in (256 * 7 + 5, 16, 3):
+        x = torch.arange(n, dtype=torch.int64).remainder(256).to(torch.uint8)
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        xd = x.to(dev)
+        check(lib().sfm_u8_to_unit_f32(ptr(xd), ptr(out), n, stream_ptr(dev)))
+        assert np.array_equal(out.cpu().numpy(), x.numpy().astype("float32") / 255)
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_simple_sfm_dataset_batched_equals_per_image(tmp_path, sp_weights, sg_weights, dev, masked):
+    from PIL import Image
+    from simplesfm_b200.matchers import Matcher
+    frames = []
+    for i in range(5):
+        Image.fromarray(_grey_u8(20 + i, shift=(i, -i))).save(tmp_path / f"im_{i}.png")
+        item = {"file_path": f"./im_{i}.png"}
+        if masked:
+            m = np.zeros((240, 320), np.uint8)
+            m[20:200, 30 + 10 * i:300] = 255
+            Image.fromarray(m).save(tmp_path / f"mask_{i}.png")
+            item["mask_path"] = f"./mask_{i}.png"
+        frames.append(item)
+    (tmp_path / "views_data.json").write_text(json.dumps({"frames": frames}))
+    kw = dict(matcher_type="super_glue", super_glue_weights_path=sg_weights, match_threshold=0.2,
+              sinkhorn_iterations=10, super_glue_batch=2, max_keypoints=256, device=dev)
+    ref = Matcher(sp_weights, 4, 0.005, extract_batch=1, **kw)
+    new = Matcher(sp_weights, 4, 0.005, extract_batch=4, decode_threads=3, **kw)
+    mask_name = "mask_path" if masked else None
+    fa, ta, na = ref.match_simple_sfm_dataset(str(tmp_path), dataset_mask_name=mask_name)
+    fb, tb, nb = new.match_simple_sfm_dataset(str(tmp_path), dataset_mask_name=mask_name)
+    assert na == nb == {i + 1: f"im_{i}.png" for i in range(5)}
+    assert all(len(f.keypoints_poses) > 20 for f in fa)
+    _same_frames(fa, fb)
+    _same_tables(ta, tb)
+    if masked:   # every keypoint lies inside its mask rectangle
+        for i, f in enumerate(fb):
+            kp = f.keypoints_poses.cpu().numpy()
+            assert (kp[:, 0] >= 30 + 10 * i).all() and (kp[:, 0] < 300).all()
+            assert (kp[:, 1] >= 20).all() and (kp[:, 1] < 200).all()
+
+
+class _FakeStream:
+    """Minimal stand-in for utils/video_streamer.py VideoStreamer: next_frame() -> (f32 image, status, path)."""
+
+    def __init__(self, images):
+        self.images, self.i = images, 0
+
+    def next_frame(self):
+        if self.i >= len(self.images):
+            return None, False, ""
+        im = self.images[self.i]
+        self.i += 1
+        return im, True, f"/video/frame_{self.i:05d}.png"
+
+
+def test_video_stream_batched_equals_per_image(sp_weights, dev):
+    from simplesfm_b200.matchers import Matcher
+    imgs = [_grey_u8(40 + i).astype("float32") / 255 for i in range(5)]
+    masks = [(np.arange(320)[None, :] > 40 * i).astype("float32") * np.ones((240, 1), "float32") for i in range(5)]
+    out = []
+    for eb in (1, 3):   # 5 frames in batches of 3: one full, one ragged
+        m = Matcher(sp_weights, 4, 0.005, matcher_type="simple", match_threshold=0.7, device=dev, extract_batch=eb)
+        out.append(m.match_video_stream(_FakeStream(imgs), vs_mask=_FakeStream(masks)))
+    (fa, ta, na), (fb, tb, nb) = out
+    assert na == nb and na[1] == "frame_00001.png" and len(na) == 5
+    _same_frames(fa, fb)
+    _same_tables(ta, tb)
+
+
+def test_unbounded_keypoints_and_mixed_shapes(sp_weights, dev):
+    """max_keypoints = -1 (one count read-back per batch) and a shape change in the middle of the stream."""
+    from simplesfm_b200.ingest import FrameExtractor
+    from simplesfm_b200.models.superpoint import SuperPoint
+    sp = SuperPoint(sp_weights, max_keypoints=-1, device=dev)
+    items = [(_grey_u8(60 + i), None) for i in range(3)] + [(_grey_u8(70 + i, 160, 240), None) for i in range(2)]
+    got = FrameExtractor(sp, batch_size=4).extract(items)
+    assert len(got) == 5
+    for (im, _), e in zip(items, got):
+        x = torch.from_numpy(im.astype("float32") / 255)[None, None].to(dev)
+        r = sp({"image": x})
+        assert torch.equal(r["keypoints"], e.keypoints) and torch.equal(r["scores"], e.scores)
+        assert torch.equal(r["descriptors"], e.descriptors)
+        assert torch.equal(e.image, x[0])
