@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--iters", type=int, default=20, help="sinkhorn_iterations (Matcher default 20)")
     ap.add_argument("--bn", default="train", choices=["train", "eval"])
     ap.add_argument("--cpu-pairs", type=int, default=2, help="pairs in the bounded CPU sample")
-    ap.add_argument("--fuse-chunks", type=int, default=16, help="Matcher chunks launched together (BN stats stay per chunk)")
+    ap.add_argument("--fuse-chunks", type=int, default=32, help="Matcher chunks launched together (BN stats stay per chunk)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

@@ -76,7 +76,7 @@ class Matcher(object):
                  precision: str = 'fp32',
                  device: str = 'cuda',
                  shard_pairs: bool = True,
-                 fuse_chunks: int = 16,
+                 fuse_chunks: int = 32,
                  superpoint_precision: str = 'fp32',
                  extract_batch: int = 8,
                  decode_threads: int = 4):
