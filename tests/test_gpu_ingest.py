@@ -125,3 +125,62 @@ def test_unbounded_keypoints_and_mixed_shapes(sp_weights, dev):
         assert torch.equal(r["keypoints"], e.keypoints) and torch.equal(r["scores"], e.scores)
         assert torch.equal(r["descriptors"], e.descriptors)
         assert torch.equal(e.image, x[0])
+
+
+def test_config3_miniature_images_to_colmap_db(tmp_path, sp_weights, sg_weights_outdoor, dev):
+    """BASELINE config 3 in miniature (generate_sparse_colmap defaults: outdoor weights, masks, batch 4, 20 Sinkhorn
+    iterations; `simple_sfm_dataset_utils.py:82-139`): image + mask files -> Matcher.match_simple_sfm_dataset ->
+    ColmapDatabaseWriter, checked against the CPU oracle run on the same decoded pixels and the oracle's blob
+    restatement of `colmap_bd_utils.py:291-372`."""
+    import sqlite3
+    import sfm_oracle as O
+    from PIL import Image
+    from simplesfm_b200.colmap_db import ColmapDatabaseWriter
+    from simplesfm_b200.matchers import Matcher
+    n, H, W = 4, 160, 240
+    frames_meta, imgs, masks = [], [], []
+    for i in range(n):
+        im = _grey_u8(90, H, W, shift=(2 * i, -3 * i))
+        m = np.zeros((H, W), np.uint8)
+        m[8:H - 8, 8 + 4 * i:W - 8] = 255
+        Image.fromarray(im).save(tmp_path / f"view_{i}.png")
+        Image.fromarray(m).save(tmp_path / f"view_{i}_mask.png")
+        frames_meta.append({"file_path": f"./view_{i}.png", "mask_path": f"./view_{i}_mask.png"})
+        imgs.append(im)
+        masks.append(m)
+    (tmp_path / "views_data.json").write_text(json.dumps({"frames": frames_meta}))
+    thr, mthr = 0.005, 0.2    # synthetic weights: the defaults 1e-4 / 0.9 would keep everything / nothing
+    m = Matcher(sp_weights, 4, thr, matcher_type="super_glue", super_glue_weights_path=sg_weights_outdoor,
+                match_threshold=mthr, sinkhorn_iterations=20, super_glue_batch=4, max_keypoints=200, device=dev)
+    frames, table, names = m.match_simple_sfm_dataset(str(tmp_path), dataset_mask_name="mask_path")
+    db = ColmapDatabaseWriter(str(tmp_path / "colmap"), images_folder_path=str(tmp_path), camera_size=(W, H))
+    db.replace_images_data(names)
+    db.replace_keypoints(names, frames)
+    db.replace_and_verificate_matches(table, names, run_verification=False)
+
+    # oracle on the same pixels
+    ofr = []
+    for im, mk in zip(imgs, masks):
+        x = torch.from_numpy(im.astype("float32") / 255)[None, None]
+        o = O.superpoint_forward(sp_weights, x, torch.from_numpy(mk > 0)[None, None], 4, thr, 200, 4)
+        ofr.append((o["descriptors"], o["keypoints"], o["scores"], x[0]))
+    otab = O.superglue_match_table(sg_weights_outdoor, ofr, O.pair_list(list(range(1, n + 1))), 4, 20, mthr, "train")
+
+    con = sqlite3.connect(str(tmp_path / "colmap" / "database.db"))
+    assert [r[0] for r in con.execute("SELECT name FROM images ORDER BY image_id")] == [f"view_{i}.png" for i in range(n)]
+    total = 0
+    for i in range(n):
+        kp = db.read_keypoints(i + 1)
+        okp = ofr[i][1].numpy()
+        assert kp.shape == (len(okp), 4) and (kp[:, 2] == 1).all() and (kp[:, 3] == 0).all()
+        assert {tuple(r) for r in kp[:, :2].tolist()} == {tuple(r) for r in okp.tolist()}
+    assert set(table) == set(otab)
+    for (a, b), ref in otab.items():
+        got = db.read_matches(int(a), int(b))
+        ka, kb_ = db.read_keypoints(int(a))[:, :2], db.read_keypoints(int(b))[:, :2]
+        oa, ob = ofr[a - 1][1].numpy(), ofr[b - 1][1].numpy()
+        assert {(tuple(ka[i]), tuple(kb_[j])) for i, j in got.tolist()} == \
+               {(tuple(oa[i]), tuple(ob[j])) for i, j in ref.tolist()}, (a, b)
+        total += len(ref)
+    assert total > 20
+    assert open(tmp_path / "colmap" / "match.txt").read().splitlines()[0] == "view_0.png view_1.png"
