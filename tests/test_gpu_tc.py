@@ -114,6 +114,36 @@ def test_superglue_bf16_match_agreement(sg_weights, dev, mode):
     assert agree >= 0.995
 
 
+@pytest.mark.parametrize("B,K0,K1", [(2, 384, 256), (3, 200, 333), (1, 128, 2048)])
+def test_fused_batchnorm_equals_standalone(sg_weights, dev, monkeypatch, B, K0, K1):
+    """Train-mode BatchNorm fused into the MLP GEMMs (moments from MLP1's epilogue, normalise + ReLU on MLP2's A
+    tiles) against the stand-alone statistics / apply kernels: same score matrix to bf16 noise, same matches.
+    (3, 200, 333) is not tile-aligned and takes the stand-alone kernels on both runs."""
+    from simplesfm_b200 import synthetic
+    from simplesfm_b200.models.superglue import SuperGlue
+    fr = synthetic.feature_scene(2 * B, max(K0, K1), seed=21)
+    data = {"descriptors0": torch.stack([fr[i][0][:, :K0] for i in range(B)]).to(dev),
+            "descriptors1": torch.stack([fr[B + i][0][:, :K1] for i in range(B)]).to(dev),
+            "keypoints0": torch.stack([fr[i][1][:K0] for i in range(B)]).to(dev),
+            "keypoints1": torch.stack([fr[B + i][1][:K1] for i in range(B)]).to(dev),
+            "scores0": torch.stack([fr[i][2][:K0] for i in range(B)]).to(dev),
+            "scores1": torch.stack([fr[B + i][2][:K1] for i in range(B)]).to(dev),
+            "image0": torch.zeros(B, 1, 480, 640), "image1": torch.zeros(B, 1, 480, 640)}
+    m = SuperGlue(sg_weights, sinkhorn_iterations=20, match_threshold=0.2, bn_mode="train", precision="bf16", device=dev)
+    fused = m(data)
+    monkeypatch.setenv("SFM_NO_BN_FUSION", "1")
+    plain = m(data)
+    monkeypatch.delenv("SFM_NO_BN_FUSION")
+    assert torch.isfinite(fused["matching_scores0"]).all()
+    agree = _agreement(fused["matches0"], plain["matches0"])
+    n = int((plain["matches0"] > -1).sum())
+    print(f"fused vs stand-alone BatchNorm B={B} K0={K0} K1={K1}: agreement {agree:.4f} over {n} matches")
+    assert n > 10
+    assert agree >= 0.99
+    both = (fused["matches0"] > -1) & (plain["matches0"] > -1)     # flips sit at the match threshold
+    torch.testing.assert_close(fused["matching_scores0"][both], plain["matching_scores0"][both], rtol=0, atol=0.05)
+
+
 def test_superglue_bf16_golden_ragged(sg_weights, dev):
     """Ragged keypoint counts (96 / 80) through the bf16 path against the reference golden matches."""
     from simplesfm_b200.models.superglue import SuperGlue
