@@ -239,54 +239,60 @@ int launch_gemm(const GemmF32& p, cudaStream_t st) {
   return SFM_OK;
 }
 
-// conv1a: one input channel.  Each thread: one pixel x 16 output channels (4 threads per pixel).
-__global__ void conv1a_kernel(const float* __restrict__ img, const float* __restrict__ w9,
-                              const float* __restrict__ bias, float* __restrict__ out,
-                              __nv_bfloat16* __restrict__ out_h, int n_img, int H, int W) {
-  __shared__ float sw[64 * 9];
-  __shared__ float sb[64];
-  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w9[i];
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) sb[i] = bias[i];
-  __syncthreads();
-  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)n_img * H * W * 4;
-  if (gid >= total) return;
-  int q = gid & 3;
-  long long pix = gid >> 2;
-  int hw = H * W;
-  int n = pix / hw, rem = pix - (long long)n * hw;
-  int y = rem / W, x = rem - y * W;
-  float v[9];
+// conv1a: one input channel, 64 output channels.  thread = (8-channel group, pixel): the group's 72 weights live
+// in registers for the whole thread (no shared-memory operand per FMA), a block walks 8 x 32 consecutive pixels
+// of the flattened image batch, and every warp store covers 4 adjacent pixels x 64 channels (NHWC, fully coalesced).
+// Same accumulation order as before (taps in (ky, kx) order), so fp32 results are unchanged.
+constexpr int C1A_PIX_PER_BLOCK = 256;
+__global__ void __launch_bounds__(256) conv1a_kernel(const float* __restrict__ img, const float* __restrict__ w9,
+                                                     const float* __restrict__ bias, float* __restrict__ out,
+                                                     __nv_bfloat16* __restrict__ out_h, int n_img, int H, int W) {
+  const int cg = threadIdx.x & 7, lp = threadIdx.x >> 3;   // channel group, pixel lane (0..31)
+  float w[8][9], b[8];
 #pragma unroll
-  for (int ky = 0; ky < 3; ky++)
+  for (int c = 0; c < 8; c++) {
+    b[c] = bias[cg * 8 + c];
 #pragma unroll
-    for (int kx = 0; kx < 3; kx++) {
-      int yy = y + ky - 1, xx = x + kx - 1;
-      v[ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? img[(long long)n * hw + yy * W + xx] : 0.f;
-    }
-  float o[16];
-#pragma unroll
-  for (int c = 0; c < 16; c++) {
-    int co = q * 16 + c;
-    float a = 0.f;
-#pragma unroll
-    for (int t = 0; t < 9; t++) a = fmaf(v[t], sw[co * 9 + t], a);
-    o[c] = fmaxf(a + sb[co], 0.f);
+    for (int t = 0; t < 9; t++) w[c][t] = w9[(cg * 8 + c) * 9 + t];
   }
-  if (out_h != nullptr) {
-    uint4* dh = reinterpret_cast<uint4*>(out_h + pix * 64 + q * 16);
+  const int hw = H * W;
+  const long long total = (long long)n_img * hw;
+  const long long p0 = (long long)blockIdx.x * C1A_PIX_PER_BLOCK;
+#pragma unroll 2
+  for (int it = 0; it < C1A_PIX_PER_BLOCK / 32; it++) {
+    const long long pix = p0 + it * 32 + lp;
+    if (pix >= total) break;
+    const int n = (int)(pix / hw), rem = (int)(pix - (long long)n * hw);
+    const int y = rem / W, x = rem - y * W;
+    const float* im = img + (long long)n * hw;
+    float v[9];
 #pragma unroll
-    for (int c = 0; c < 2; c++) {
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(o[c * 8], o[c * 8 + 1]), h1 = __floats2bfloat162_rn(o[c * 8 + 2], o[c * 8 + 3]),
-                     h2 = __floats2bfloat162_rn(o[c * 8 + 4], o[c * 8 + 5]), h3 = __floats2bfloat162_rn(o[c * 8 + 6], o[c * 8 + 7]);
-      dh[c] = make_uint4(*reinterpret_cast<unsigned*>(&h0), *reinterpret_cast<unsigned*>(&h1),
-                         *reinterpret_cast<unsigned*>(&h2), *reinterpret_cast<unsigned*>(&h3));
+    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+      for (int kx = 0; kx < 3; kx++) {
+        const int yy = y + ky - 1, xx = x + kx - 1;
+        v[ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? im[yy * W + xx] : 0.f;
+      }
+    float o[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      float a = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; t++) a = fmaf(v[t], w[c][t], a);
+      o[c] = fmaxf(a + b[c], 0.f);
     }
-    return;
+    if (out_h != nullptr) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]),
+                     h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
+      *reinterpret_cast<uint4*>(out_h + pix * 64 + cg * 8) =
+          make_uint4(*reinterpret_cast<unsigned*>(&h0), *reinterpret_cast<unsigned*>(&h1),
+                     *reinterpret_cast<unsigned*>(&h2), *reinterpret_cast<unsigned*>(&h3));
+    } else {
+      float4* dst = reinterpret_cast<float4*>(out + pix * 64 + cg * 8);
+      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
   }
-  float4* dst = reinterpret_cast<float4*>(out + pix * 64 + q * 16);
-#pragma unroll
-  for (int c = 0; c < 4; c++) dst[c] = make_float4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]);
 }
 
 __global__ void maxpool2_kernel(const float4* __restrict__ in, float4* __restrict__ out, int n_img, int H, int W,
@@ -319,9 +325,9 @@ int conv3x3_f32(const GemmF32& p, cudaStream_t st) { return launch_gemm<2>(p, st
 
 int conv1a_f32(const float* img, const float* w9, const float* bias, float* out, __nv_bfloat16* out_h, int n_img,
                int H, int W, cudaStream_t st) {
-  long long total = (long long)n_img * H * W * 4;
+  long long total = (long long)n_img * H * W;
   if (total == 0) return SFM_OK;
-  conv1a_kernel<<<cdiv(total, 256), 256, 0, st>>>(img, w9, bias, out, out_h, n_img, H, W);
+  conv1a_kernel<<<cdiv(total, C1A_PIX_PER_BLOCK), 256, 0, st>>>(img, w9, bias, out, out_h, n_img, H, W);
   SFM_LAUNCH_CHECK();
   return SFM_OK;
 }

@@ -249,30 +249,42 @@ __device__ __forceinline__ unsigned f2ord(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-__global__ void rank_sort_kernel(const int* __restrict__ cand_pix, const float* __restrict__ cand_score,
-                                 const int* __restrict__ counts, int cap, int max_kp, int W, int out_cap,
-                                 float* __restrict__ kpts_xy, float* __restrict__ scores_out,
-                                 int* __restrict__ out_counts) {
+// 64 candidates per block (a few thousand candidates per image must still fill 148 SMs); the keys of all
+// candidates stream through a 256-entry shared tile that every thread scans four at a time.
+constexpr int RANK_THREADS = 64;
+__global__ void __launch_bounds__(RANK_THREADS) rank_sort_kernel(const int* __restrict__ cand_pix,
+                                                                const float* __restrict__ cand_score,
+                                                                const int* __restrict__ counts, int cap, int max_kp,
+                                                                int W, int out_cap, float* __restrict__ kpts_xy,
+                                                                float* __restrict__ scores_out,
+                                                                int* __restrict__ out_counts) {
   int img = blockIdx.y;
   int C = min(counts[img], cap);
   int keep = (max_kp >= 0 && max_kp < C) ? max_kp : C;
   keep = min(keep, out_cap);
   if (blockIdx.x == 0 && threadIdx.x == 0) out_counts[img] = keep;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (blockIdx.x * blockDim.x >= C) return;
+  int i = blockIdx.x * RANK_THREADS + threadIdx.x;
+  if (blockIdx.x * RANK_THREADS >= C) return;
   const float* sc = cand_score + (long long)img * cap;
   const int* px = cand_pix + (long long)img * cap;
   unsigned ki = i < C ? f2ord(sc[i]) : 0u;
-  __shared__ unsigned tile[256];
+  __shared__ __align__(16) unsigned tile[256];
   int rank = 0;
   for (int base = 0; base < C; base += 256) {
-    int j = base + threadIdx.x;
-    tile[threadIdx.x] = j < C ? f2ord(sc[j]) : 0u;
+#pragma unroll
+    for (int q = 0; q < 256 / RANK_THREADS; q++) {
+      int j = base + q * RANK_THREADS + threadIdx.x;
+      tile[q * RANK_THREADS + threadIdx.x] = j < C ? f2ord(sc[j]) : 0u;   // 0 never outranks a real key
+    }
     __syncthreads();
-    int lim = min(256, C - base);
-    for (int t = 0; t < lim; t++) {
-      unsigned kj = tile[t];
-      rank += (kj > ki) || (kj == ki && (base + t) < i);
+    // entries before candidate i win ties (pixel-ascending order): count `>=` there and `>` after it
+    const int nge = min(max(i - base, 0), 256);   // tile entries [0, nge) precede i
+    for (int t = 0; t < 256; t += 4) {
+      const uint4 k4 = *reinterpret_cast<const uint4*>(&tile[t]);
+      rank += (k4.x > ki) + (k4.y > ki) + (k4.z > ki) + (k4.w > ki);
+      if (t < nge)
+        rank += (t < nge && k4.x == ki) + (t + 1 < nge && k4.y == ki) + (t + 2 < nge && k4.z == ki) +
+                (t + 3 < nge && k4.w == ki);
     }
     __syncthreads();
   }
@@ -403,8 +415,8 @@ int sp_select(const float* nms, const unsigned char* mask, int n_img, int H, int
 int sp_rank_sort(const int* cand_pix, const float* cand_score, const int* counts, int n_img, int cap, int max_kp,
                  int W, int out_cap, float* kpts_xy, float* scores_out, int* out_counts, cudaStream_t st) {
   if (n_img == 0) return SFM_OK;
-  dim3 grid(cdiv(cap, 256), n_img);
-  rank_sort_kernel<<<grid, 256, 0, st>>>(cand_pix, cand_score, counts, cap, max_kp, W, out_cap, kpts_xy, scores_out,
+  dim3 grid(cdiv(cap, RANK_THREADS), n_img);
+  rank_sort_kernel<<<grid, RANK_THREADS, 0, st>>>(cand_pix, cand_score, counts, cap, max_kp, W, out_cap, kpts_xy, scores_out,
                                          out_counts);
   SFM_LAUNCH_CHECK();
   return SFM_OK;
