@@ -337,6 +337,27 @@ __global__ void __launch_bounds__(256) sks_prologue_kernel(float* __restrict__ S
 }
 
 // fused sweep: A for the rows of this block, then the block's column sums of K_ij A_i
+// Sum R per-lane values (one per row) across the 32 lanes of a warp with R - 1 + log2(32 / R) shuffles instead of
+// 5 R: every round the lanes swap half of their values with a partner and keep the other half.  On return v[0]
+// of lane L is the warp total of row L >> log2(32 / R).
+template <int R>
+__device__ __forceinline__ float transpose_reduce(float (&v)[R], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = R; n > 1; n >>= 1, off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < n / 2; k++) {
+      const float send = hi ? v[k] : v[k + n / 2];
+      const float keep = hi ? v[k + n / 2] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];
+}
+
 template <int G, bool H16>
 __global__ void __launch_bounds__(256, 2) sks_fused_kernel(const void* __restrict__ Kp, int N, int M, float ealpha,
                                                         const float* __restrict__ kb, const float* __restrict__ Bv,
@@ -348,6 +369,7 @@ __global__ void __launch_bounds__(256, 2) sks_fused_kernel(const void* __restric
   constexpr int RS = (H16 ? 32 : 16) / G;
   constexpr int XW = H16 ? 2 : 4;   // registers per 4 matrix elements
   __shared__ float red[2][8][RS];
+  __shared__ float sai[2][RS];
   __shared__ float red_bin[8];
   const int b = blockIdx.y, blk = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -417,6 +439,7 @@ __global__ void __launch_bounds__(256, 2) sks_fused_kernel(const void* __restric
         }
       }
     }
+    float rs[RS];
 #pragma unroll
     for (int r = 0; r < RS; r++) {
       float sacc = 0.f;
@@ -427,20 +450,28 @@ __global__ void __launch_bounds__(256, 2) sks_fused_kernel(const void* __restric
 #pragma unroll
         for (int e = 0; e < 4; e++) sacc = fmaf(f[e], bj[4 * g + e], sacc);
       }
-      sacc = warp_sum(sacc);
-      if (lane == 0) red[par][warp][r] = sacc;
+      rs[r] = sacc;
+    }
+    {
+      const float tot = transpose_reduce<RS>(rs, lane);
+      constexpr int LPR = 32 / RS;   // lanes that end up with the same row
+      if ((lane & (LPR - 1)) == 0) red[par][warp][lane / LPR] = tot;
+    }
+    __syncthreads();
+    if (tid < RS) {   // one thread per row: A_i (the 8 warp partials, the dustbin term, one division)
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; w++) tot += red[par][w][tid];
+      if (H16) tot *= K16_INV;
+      const bool rok = i0 + tid < N;
+      const float ai = rok ? mu / fmaf(kbb[rok ? i0 + tid : 0], bbin, tot) : 0.f;
+      sai[par][tid] = ai;
+      if (rok) Ab[i0 + tid] = ai;
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < RS; r++) {   // one scaling factor live at a time: keeps the step inside 128 registers
-      float tot = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; w++) tot += red[par][w][r];
-      if (H16) tot *= K16_INV;
-      const bool rok = i0 + r < N;
-      const float kbr = rok ? kbb[i0 + r] : 1.f;
-      const float ai = rok ? mu / fmaf(kbr, bbin, tot) : 0.f;
-      if (tid == r && rok) Ab[i0 + r] = ai;
+    for (int r = 0; r < RS; r++) {
+      const float ai = sai[par][r];
 #pragma unroll
       for (int g = 0; g < G; g++) {
         float f[4];
