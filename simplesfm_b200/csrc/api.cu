@@ -445,6 +445,7 @@ int ot_prepare(const float* scores, int B, int N, int M, float alpha, int iters,
     s.fast = true;
     s.fused_part = b.fused;
     s.kb = b.kb;
+    s.col_idx = b.idx1;
   }
   return sinkhorn_run(s, st);
 }

@@ -358,7 +358,10 @@ __device__ __forceinline__ float transpose_reduce(float (&v)[R], int lane) {
   return v[0];
 }
 
-template <int G, bool H16>
+// LAST (final iteration): the sweep also tracks, per column, the largest K_ij A_i of its 64 rows and the row it
+// came from -- the column arg-max of the assignment (first index on ties) -- so that matching needs no separate
+// pass over the matrix for it.  part then holds [sums | maxima | indices], each [B, nblk, M].
+template <int G, bool H16, bool LAST>
 __global__ void __launch_bounds__(256, 2) sks_fused_kernel(const void* __restrict__ Kp, int N, int M, float ealpha,
                                                         const float* __restrict__ kb, const float* __restrict__ Bv,
                                                         float* __restrict__ Av, float* __restrict__ part, float mu,
@@ -401,8 +404,17 @@ __global__ void __launch_bounds__(256, 2) sks_fused_kernel(const void* __restric
     }
   }
   float cs[4 * G];
+  [[maybe_unused]] float bv[LAST ? 4 * G : 1];
+  [[maybe_unused]] int bidx[LAST ? 4 * G : 1];
 #pragma unroll
   for (int c = 0; c < 4 * G; c++) cs[c] = 0.f;
+  if (LAST) {
+#pragma unroll
+    for (int c = 0; c < 4 * G; c++) {
+      bv[LAST ? c : 0] = 0.f;            // K A > 0 for every real entry
+      bidx[LAST ? c : 0] = 0x7fffffff;
+    }
+  }
   const int row0 = blk * FUSED_RB;
   int par = 0;
   auto unpack = [](const uint32_t* xr, float* f) {   // 4 matrix elements of one (row, g) slot
@@ -477,7 +489,31 @@ __global__ void __launch_bounds__(256, 2) sks_fused_kernel(const void* __restric
         float f[4];
         unpack(x[r][g], f);
 #pragma unroll
-        for (int e = 0; e < 4; e++) cs[4 * g + e] = fmaf(f[e], ai, cs[4 * g + e]);
+        for (int e = 0; e < 4; e++) {
+          cs[4 * g + e] = fmaf(f[e], ai, cs[4 * g + e]);
+          if (LAST) {
+            const float z = f[e] * ai;
+            if (z > bv[LAST ? 4 * g + e : 0]) {   // strict: rows ascend, so ties keep the first row
+              bv[LAST ? 4 * g + e : 0] = z;
+              bidx[LAST ? 4 * g + e : 0] = i0 + r;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (LAST) {
+    const long long plane = (long long)gridDim.y * gridDim.x * M;
+    float* pm = part + plane + ((long long)b * gridDim.x + blk) * M;
+    int* pi = reinterpret_cast<int*>(part + 2 * plane) + ((long long)b * gridDim.x + blk) * M;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      const int col = (g * 256 + tid) * 4;
+      if (col < M) {
+        *reinterpret_cast<float4*>(pm + col) = make_float4(bv[LAST ? 4 * g : 0], bv[LAST ? 4 * g + 1 : 0],
+                                                           bv[LAST ? 4 * g + 2 : 0], bv[LAST ? 4 * g + 3 : 0]);
+        *reinterpret_cast<int4*>(pi + col) = make_int4(bidx[LAST ? 4 * g : 0], bidx[LAST ? 4 * g + 1 : 0],
+                                                       bidx[LAST ? 4 * g + 2 : 0], bidx[LAST ? 4 * g + 3 : 0]);
       }
     }
   }
@@ -496,7 +532,7 @@ __global__ void __launch_bounds__(256, 2) sks_fused_kernel(const void* __restric
 __global__ void __launch_bounds__(256) sks_combine_kernel(const float* __restrict__ part, int nblk, int N, int M,
                                                           float ealpha, const float* __restrict__ kb,
                                                           const float* __restrict__ Av, float* __restrict__ Bv,
-                                                          float nu, float nu_bin) {
+                                                          float nu, float nu_bin, int* __restrict__ col_idx) {
   __shared__ float red[8];
   const int b = blockIdx.y;
   const float* Ab = Av + (long long)b * (N + 1);
@@ -523,6 +559,21 @@ __global__ void __launch_bounds__(256) sks_combine_kernel(const float* __restric
   float tot = ealpha * an;
   for (int k = 0; k < nblk; k++) tot += p[(long long)k * M];
   Bb[j] = nu / tot;
+  if (col_idx != nullptr) {   // last iteration: column arg-max over the row blocks (blocks ascend: first index wins ties)
+    const long long plane = (long long)gridDim.y * nblk * M;
+    const float* pm = p + plane;
+    const int* pi = reinterpret_cast<const int*>(part + 2 * plane) + (long long)b * nblk * M + j;
+    float best = 0.f;
+    int bi = 0x7fffffff;
+    for (int k = 0; k < nblk; k++) {
+      const float v = pm[(long long)k * M];
+      if (v > best) {
+        best = v;
+        bi = pi[(long long)k * M];
+      }
+    }
+    col_idx[(long long)b * M + j] = bi == 0x7fffffff ? 0 : bi;
+  }
 }
 
 // row argmax of K_ij B_j (== argmax of the log assignment); matching score = K A B (N + M)
@@ -839,7 +890,7 @@ size_t sinkhorn_partial_floats(int B, int N, int M, int* R_out) {
   if (R_out) *R_out = R;
   return (size_t)B * R * (M + 1) * 2;
 }
-size_t sinkhorn_fused_floats(int B, int N, int M) { return (size_t)B * cdiv(N, FUSED_RB) * M; }
+size_t sinkhorn_fused_floats(int B, int N, int M) { return (size_t)3 * B * cdiv(N, FUSED_RB) * M; }   // sums | maxima | rows
 bool sinkhorn_use_scaling(const SinkhornArgs& a) {
   return a.fast && a.fused_part != nullptr && a.kb != nullptr && a.M % 4 == 0 && a.M <= 4096 && a.iters > 0;
 }
@@ -869,16 +920,15 @@ int sinkhorn_run(const SinkhornArgs& a, cudaStream_t st) {
     const bool h16 = a.k16 != nullptr;
     const void* Kit = h16 ? (const void*)a.k16 : (const void*)K;
     for (int it = 0; it < a.iters; it++) {
-#define SKS_LAUNCH(G, H) sks_fused_kernel<G, H><<<fgrid, 256, 0, st>>>(Kit, N, M, ealpha, a.kb, a.v, a.u, a.fused_part, mu, mu_bin)
-      if (M <= 1024) {
-        if (h16) SKS_LAUNCH(1, true); else SKS_LAUNCH(1, false);
-      } else if (M <= 2048) {
-        if (h16) SKS_LAUNCH(2, true); else SKS_LAUNCH(2, false);
-      } else {
-        if (h16) SKS_LAUNCH(4, true); else SKS_LAUNCH(4, false);
-      }
+      const bool last = a.col_idx != nullptr && it + 1 == a.iters;
+#define SKS_LAUNCH(G, H, L) sks_fused_kernel<G, H, L><<<fgrid, 256, 0, st>>>(Kit, N, M, ealpha, a.kb, a.v, a.u, a.fused_part, mu, mu_bin)
+#define SKS_PICK(G) { if (h16) { if (last) SKS_LAUNCH(G, true, true); else SKS_LAUNCH(G, true, false); } \
+                      else { if (last) SKS_LAUNCH(G, false, true); else SKS_LAUNCH(G, false, false); } }
+      if (M <= 1024) SKS_PICK(1) else if (M <= 2048) SKS_PICK(2) else SKS_PICK(4)
+#undef SKS_PICK
 #undef SKS_LAUNCH
-      sks_combine_kernel<<<cg, 256, 0, st>>>(a.fused_part, nblk, N, M, ealpha, a.kb, a.u, a.v, mu, nu_bin);
+      sks_combine_kernel<<<cg, 256, 0, st>>>(a.fused_part, nblk, N, M, ealpha, a.kb, a.u, a.v, mu, nu_bin,
+                                             last ? a.col_idx : nullptr);
     }
     count_launches(2 + 2 * a.iters);
     SFM_CUDA(cudaGetLastError());
@@ -933,8 +983,9 @@ int sinkhorn_match(const SinkhornArgs& a, float thr, float* max0, int* idx0, flo
   if (sinkhorn_use_scaling(a)) {
     // a.S now holds K, a.u = A, a.v = B: assignment probabilities are K A B (N + M)
     sks_row_argmax_kernel<<<dim3(cdiv(N, 8), B), 256, 0, st>>>(a.S, N, M, a.u, a.v, (float)N + (float)M, max0, idx0);
-    sk_col_kernel<2, false><<<dim3(cdiv(M, 128), a.R, B), 256, 0, st>>>(a.S, N, M, a.alpha, a.u, a.v, nullptr, a.part,
-                                                                        a.counters, a.R, 0.f, 0.f, max1, idx1);
+    if (a.col_idx != idx1 || a.iters == 0)   // column arg-max not produced by the last sweep
+      sk_col_kernel<2, false><<<dim3(cdiv(M, 128), a.R, B), 256, 0, st>>>(a.S, N, M, a.alpha, a.u, a.v, nullptr, a.part,
+                                                                          a.counters, a.R, 0.f, 0.f, max1, idx1);
     mutual_kernel<<<mgrid, 256, 0, st>>>(max0, idx0, idx1, N, M, thr, 1, matches0, matches1, mscores0, mscores1);
     SFM_LAUNCH_CHECK_N(3);
     return SFM_OK;

@@ -34,7 +34,8 @@ struct SinkhornArgs {
   float* part;      // [B, R, M+1, 2] column partials
   int* counters;    // [B, colblocks] zero-initialised, self-resetting
   int R;            // row splits of the column pass
-  float* fused_part = nullptr;  // [B, ceil(N/64), M] column partial sums of the fused single-read sweep
+  float* fused_part = nullptr;  // 3 x [B, ceil(N/64), M]: column partial sums (+ maxima, rows in the last sweep)
+  int* col_idx = nullptr;       // optional [B, M]: column arg-max of the assignment, written by the last sweep
   float* kb = nullptr;          // [B, N] dustbin-column factors exp(alpha - rowmax) of the scaling form
   __half* k16 = nullptr;        // optional [B, N, M] fp16 copy of the scaling-form matrix the iterations stream
   int sub_batch = 0;  // pairs per L2-resident sweep group (0 = auto)
