@@ -244,6 +244,7 @@ int sg_forward(sfm_ctx* h, const SgCall& c, void* ws, size_t ws_bytes, bool dry,
   s.fused_part = b.sk_fused;
   s.kb = b.sk_kb;
   s.col_idx = b.idx1;
+  s.rowmax = b.max0;
   s.k16 = reinterpret_cast<__half*>(b.sk_k16f);
   ProfScope ps(h, SFM_PROF_SINKHORN, st);
   SFM_TRY(sinkhorn_run(s, st));

@@ -312,8 +312,11 @@ constexpr int FUSED_RB = 64;
 // per sweep; the 2^14 keeps entries down to e^-19 of the row maximum in fp16's normal range, 11-bit mantissa);
 // the final arg-max passes still read the fp32 K.
 constexpr float K16_SCALE = 16384.f, K16_INV = 1.f / 16384.f;
+// With rowmax != nullptr (and k16) the score matrix is left untouched: only the fp16 copy and c_i are written, the
+// final row arg-max works on S + log B directly.
 __global__ void __launch_bounds__(256) sks_prologue_kernel(float* __restrict__ S, int N, int M, float alpha,
-                                                           float* __restrict__ kb, __half* __restrict__ k16) {
+                                                           float* __restrict__ kb, __half* __restrict__ k16,
+                                                           float* __restrict__ rowmax) {
   const int b = blockIdx.y;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -327,13 +330,16 @@ __global__ void __launch_bounds__(256) sks_prologue_kernel(float* __restrict__ S
     for (int j = lane * 2; j < M; j += 64) {   // M % 4 == 0
       const float2 sv = *reinterpret_cast<const float2*>(sr + j);
       const float e0 = __expf(sv.x - m), e1 = __expf(sv.y - m);
-      *reinterpret_cast<float2*>(sr + j) = make_float2(e0, e1);
+      if (rowmax == nullptr) *reinterpret_cast<float2*>(sr + j) = make_float2(e0, e1);
       *reinterpret_cast<__half2*>(hr + j) = __floats2half2_rn(e0 * K16_SCALE, e1 * K16_SCALE);
     }
   } else {
     for (int j = lane; j < M; j += 32) sr[j] = __expf(sr[j] - m);
   }
-  if (lane == 0) kb[(long long)b * N + row] = __expf(alpha - m);
+  if (lane == 0) {
+    kb[(long long)b * N + row] = __expf(alpha - m);
+    if (rowmax != nullptr) rowmax[(long long)b * N + row] = m;
+  }
 }
 
 // fused sweep: A for the rows of this block, then the block's column sums of K_ij A_i
@@ -608,6 +614,48 @@ __global__ void __launch_bounds__(256) sks_row_argmax_kernel(const float* __rest
   if (lane == 0) {
     max0[(long long)b * N + row] = best * Av[(long long)b * (N + 1) + row] * scale;   // probability, not log
     idx0[(long long)b * N + row] = bi == 0x7fffffff ? 0 : bi;
+  }
+}
+
+// Same on the untouched score matrix: argmax_j K_ij B_j = argmax_j (S_ij + log B_j); cmax holds c_i on entry and is
+// overwritten with the matching score exp(S_ij + log B_j - c_i) A_i (N + M).  logB: [B, M + 1].
+__global__ void log_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = logf(in[i]);
+}
+__global__ void __launch_bounds__(256) sks_row_argmax_s_kernel(const float* __restrict__ S, int N, int M,
+                                                               const float* __restrict__ Av,
+                                                               const float* __restrict__ logB, float scale,
+                                                               float* __restrict__ cmax_max0, int* __restrict__ idx0) {
+  const int b = blockIdx.y;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* sr = S + ((long long)b * N + row) * M;
+  const float* lb = logB + (long long)b * (M + 1);
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = lane * 4; j < M; j += 128) {   // M % 4 == 0
+    const float4 sv = *reinterpret_cast<const float4*>(sr + j);
+    const float z0 = sv.x + lb[j], z1 = sv.y + lb[j + 1], z2 = sv.z + lb[j + 2], z3 = sv.w + lb[j + 3];
+    if (z0 > best) { best = z0; bi = j; }
+    if (z1 > best) { best = z1; bi = j + 1; }
+    if (z2 > best) { best = z2; bi = j + 2; }
+    if (z3 > best) { best = z3; bi = j + 3; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (b2 > best || (b2 == best && i2 < bi)) {
+      best = b2;
+      bi = i2;
+    }
+  }
+  if (lane == 0) {
+    const long long r = (long long)b * N + row;
+    cmax_max0[r] = __expf(best - cmax_max0[r]) * Av[(long long)b * (N + 1) + row] * scale;
+    idx0[r] = bi == 0x7fffffff ? 0 : bi;
   }
 }
 
@@ -913,7 +961,8 @@ int sinkhorn_run(const SinkhornArgs& a, cudaStream_t st) {
     const float ealpha = expf(a.alpha);
     const float mu = 1.0f / ((float)N + (float)M), mu_bin = (float)M * mu, nu_bin = (float)N * mu;
     float* K = const_cast<float*>(a.S);   // the score matrix is overwritten by K = exp(S - rowmax)
-    sks_prologue_kernel<<<dim3(cdiv(N, 8), B), 256, 0, st>>>(K, N, M, a.alpha, a.kb, a.k16);
+    sks_prologue_kernel<<<dim3(cdiv(N, 8), B), 256, 0, st>>>(K, N, M, a.alpha, a.kb, a.k16,
+                                                             a.k16 != nullptr ? a.rowmax : nullptr);
     fill_kernel<<<cdiv(nv, 256), 256, 0, st>>>(a.v, nv, 1.f);   // B = exp(v) = 1
     dim3 fgrid(nblk, B);
     dim3 cg(cdiv(M, 256) + 1, B);
@@ -982,7 +1031,16 @@ int sinkhorn_match(const SinkhornArgs& a, float thr, float* max0, int* idx0, flo
   dim3 mgrid(cdiv(N > M ? N : M, 256), B);
   if (sinkhorn_use_scaling(a)) {
     // a.S now holds K, a.u = A, a.v = B: assignment probabilities are K A B (N + M)
-    sks_row_argmax_kernel<<<dim3(cdiv(N, 8), B), 256, 0, st>>>(a.S, N, M, a.u, a.v, (float)N + (float)M, max0, idx0);
+    if (a.k16 != nullptr && a.rowmax != nullptr && a.rowmax == max0) {
+      // the score matrix was left untouched (the iterations ran on the fp16 copy): S + log B, c_i from max0
+      const long long nv = (long long)B * (M + 1);
+      log_kernel<<<cdiv(nv, 256), 256, 0, st>>>(a.v, a.part, nv);
+      sks_row_argmax_s_kernel<<<dim3(cdiv(N, 8), B), 256, 0, st>>>(a.S, N, M, a.u, a.part, (float)N + (float)M, max0,
+                                                                   idx0);
+      count_launches(1);
+    } else {
+      sks_row_argmax_kernel<<<dim3(cdiv(N, 8), B), 256, 0, st>>>(a.S, N, M, a.u, a.v, (float)N + (float)M, max0, idx0);
+    }
     if (a.col_idx != idx1 || a.iters == 0)   // column arg-max not produced by the last sweep
       sk_col_kernel<2, false><<<dim3(cdiv(M, 128), a.R, B), 256, 0, st>>>(a.S, N, M, a.alpha, a.u, a.v, nullptr, a.part,
                                                                           a.counters, a.R, 0.f, 0.f, max1, idx1);

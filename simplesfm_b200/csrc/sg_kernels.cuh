@@ -35,6 +35,7 @@ struct SinkhornArgs {
   int* counters;    // [B, colblocks] zero-initialised, self-resetting
   int R;            // row splits of the column pass
   float* fused_part = nullptr;  // 3 x [B, ceil(N/64), M]: column partial sums (+ maxima, rows in the last sweep)
+  float* rowmax = nullptr;      // optional [B, N]: with k16, keeps S intact and stores the row maxima here (pass max0)
   int* col_idx = nullptr;       // optional [B, M]: column arg-max of the assignment, written by the last sweep
   float* kb = nullptr;          // [B, N] dustbin-column factors exp(alpha - rowmax) of the scaling form
   __half* k16 = nullptr;        // optional [B, N, M] fp16 copy of the scaling-form matrix the iterations stream
