@@ -135,47 +135,70 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
                   k != 0);
         umma_commit(&bars->s_full[t]);
       };
-      int g = 0, it = 0;
+      // Issue order follows a STAGGERED schedule: tile 1 runs half a K/V step behind tile 0 (its softmax group
+      // starts late, see below), so that one group's exponentials overlap the other group's TMEM load / maximum /
+      // waits.  Per global step g:  S0(g+1) | PV1(g-1) | S1(g+1) | PV0(g)  -- each behind the barrier that fires
+      // next in that schedule, so the issuer never couples the two groups back into lock-step.
+      struct Cursor { int u, it, j, n_kv; bool valid; };
+      auto advance = [&](Cursor& c) {
+        if (++c.j == c.n_kv) {
+          c.u += gridDim.x;
+          c.it++;
+          c.j = 0;
+          c.valid = c.u < n_units;
+          if (c.valid) c.n_kv = decode_unit<NT>(p, c.u, units0, qt0, qt1).n_kv;
+        }
+      };
+      auto issue_pv = [&](int t, int g, bool first) {
+        mbar_wait(&bars->p_full[t], g & 1);
+        tc_fence_after();
+        const uint64_t vd = umma_desc_advance(v_desc0, (g % KV_STAGES) * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; k++)  // 16 keys per step: 16 V rows = 2048 bytes, P advances 8 columns
+          umma_ts(tmem + COL_O + t * 64, tmem + COL_P + t * 64 + k * 8, umma_desc_advance(vd, k * 2048), idesc_o,
+                  (first ? 0 : 1) | k);
+        umma_commit(&bars->o_full[t]);
+      };
+      Cursor cur{(int)blockIdx.x, 0, 0, decode_unit<NT>(p, blockIdx.x, units0, qt0, qt1).n_kv, true};
       // very first S of this CTA
       mbar_wait(&bars->q_full[0], 0);
       mbar_wait(&bars->kv_full[0], 0);
       tc_fence_after();
       for (int t = 0; t < NT; t++) issue_s(t, 0, 0);
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, it++) {
-        const Unit w = decode_unit<NT>(p, u, units0, qt0, qt1);
-        const bool has_next = u + (int)gridDim.x < n_units;
-        for (int j = 0; j < w.n_kv; j++, g++) {
-          const int s = g % KV_STAGES;
-          // (1) as soon as a warpgroup has pulled S_t(g) into registers its TMEM region is free again: issue
-          //     S_t(g+1) -- the next K/V step of this unit or step 0 of the next unit -- right away
-          const bool last = j + 1 == w.n_kv;
-          if (!last || has_next) {
-            const int s1 = (g + 1) % KV_STAGES;
-            const int qb1 = last ? ((it + 1) & 1) : (it & 1);
-            if (last) mbar_wait(&bars->q_full[qb1], ((it + 1) >> 1) & 1);
+      bool prev_first = false;   // step g-1 was the first of its unit (its P V overwrites O)
+      int g = 0;
+      for (; cur.valid; g++) {
+        Cursor nxt = cur;
+        advance(nxt);
+        const bool cur_first = cur.j == 0, cur_last = cur.j + 1 == cur.n_kv;
+        const int s1 = (g + 1) % KV_STAGES;
+        // S of step g+1 (next K/V tile of this unit, or tile 0 of the next unit with its own Q buffer)
+        auto issue_next_s = [&](int t) {
+          if (!nxt.valid) return;
+          if (t == 0) {
+            if (nxt.j == 0) mbar_wait(&bars->q_full[nxt.it & 1], (nxt.it >> 1) & 1);
             mbar_wait(&bars->kv_full[s1], ((g + 1) / KV_STAGES) & 1);
-            for (int t = 0; t < NT; t++) {
-              mbar_wait(&bars->s_free[t], g & 1);
-              tc_fence_after();
-              issue_s(t, qb1, s1);
-            }
           }
-          // all S MMAs that read this unit's Q buffer have been issued: release it when they complete
-          if (last) umma_commit(&bars->q_empty[it & 1]);
-          // (2) P_t(g) written (much later): accumulate O_t += P_t V_j.  j == 0 overwrites O_t: the group
-          //     finished reading the previous unit's O_t before it arrived on p_full (program order).
-          for (int t = 0; t < NT; t++) {
-            mbar_wait(&bars->p_full[t], g & 1);
-            tc_fence_after();
-            const uint64_t vd = umma_desc_advance(v_desc0, s * TILE_BYTES);
-#pragma unroll
-            for (int k = 0; k < 8; k++)  // 16 keys per step: 16 V rows = 2048 bytes, P advances 8 columns
-              umma_ts(tmem + COL_O + t * 64, tmem + COL_P + t * 64 + k * 8, umma_desc_advance(vd, k * 2048), idesc_o,
-                      (j | k) != 0);
-            umma_commit(&bars->o_full[t]);
-          }
-          umma_commit(&bars->kv_empty[s]);
+          mbar_wait(&bars->s_free[t], g & 1);
+          tc_fence_after();
+          issue_s(t, nxt.it & 1, s1);
+        };
+        issue_next_s(0);
+        if (NT > 1 && g > 0) {
+          issue_pv(NT - 1, g - 1, prev_first);
+          umma_commit(&bars->kv_empty[(g - 1) % KV_STAGES]);   // both tiles are done with K/V stage g-1
         }
+        for (int t = 1; t < NT; t++) issue_next_s(t);
+        // all S MMAs that read this unit's Q buffer have been issued (the next step belongs to another unit)
+        if (cur_last) umma_commit(&bars->q_empty[cur.it & 1]);
+        issue_pv(0, g, cur_first);
+        if (NT == 1) umma_commit(&bars->kv_empty[g % KV_STAGES]);
+        prev_first = cur_first;
+        cur = nxt;
+      }
+      if (NT > 1 && g > 0) {
+        issue_pv(NT - 1, g - 1, prev_first);
+        umma_commit(&bars->kv_empty[(g - 1) % KV_STAGES]);
       }
     }
   } else {
@@ -186,6 +209,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     const float c = 0.125f * 1.4426950408889634f;  // log2(e) / sqrt(64)
     int g = 0;
+    // tile 1 starts after tile 0 has produced its first probability tile: half a step of lag (see the issuer)
+    if (NT > 1 && t == 1 && p.stagger) mbar_wait(&bars->p_full[0], 0);
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
     const Unit w = decode_unit<NT>(p, u, units0, qt0, qt1);
     const int Nk = w.Nk, n_kv = w.n_kv;
@@ -325,14 +350,17 @@ int tc_attention(const TcAttn& p, cudaStream_t st) {
   CUtensorMap map;
   SFM_TRY(make_tmap_bf16(&map, p.qkv, p.rows_total, 768, 768, 128));
   static int nt = getenv("SFM_ATT_NT") ? atoi(getenv("SFM_ATT_NT")) : 2;
+  static int stagger = getenv("SFM_ATT_STAGGER") ? atoi(getenv("SFM_ATT_STAGGER")) : 1;
+  TcAttn q = p;
+  q.stagger = stagger;
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
     SFM_CUDA(cudaGetDevice(&dev));
     SFM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  if (nt == 1) return launch_att<1>(p, map, num_sms, st);
-  return launch_att<2>(p, map, num_sms, st);
+  if (nt == 1) return launch_att<1>(q, map, num_sms, st);
+  return launch_att<2>(q, map, num_sms, st);
 }
 
 }  // namespace tc

@@ -71,6 +71,7 @@ struct TcAttn {
   int B = 0;
   int Nq[2] = {0, 0}, Nk[2] = {0, 0};
   long long q_row0[2] = {0, 0}, k_row0[2] = {0, 0};
+  int stagger = 1;   // tile 1 of a CTA runs half a K/V step behind tile 0 (ping-pong on the MUFU pipe)
 };
 int tc_attention(const TcAttn& p, cudaStream_t st);
 
