@@ -19,6 +19,6 @@ python tools/prof_forward.py 40 2048 1 > /dev/null 2>&1 && \
   ncu --set full --clock-control none -k regex:sks_ -c 3 -o gpurun_out/r1_sinkhorn_kernels -f \
       python tools/prof_forward.py 40 2048 1 > gpurun_out/ncu_sk.log 2>&1; echo "sk full rc=$?"
 python tools/prof_superpoint.py bf16 > gpurun_out/plain_sp.log 2>&1 && \
-  ncu --set full --clock-control none --launch-skip 40 -c 40 -o gpurun_out/r1_superpoint_kernels -f \
+  ncu --set full --clock-control none -c 22 -o gpurun_out/r1_superpoint_kernels -f \
       python tools/prof_superpoint.py bf16 > gpurun_out/ncu_sp.log 2>&1; echo "sp full rc=$?"
 tail -1 gpurun_out/r1_pytest_gpu.log; tail -1 gpurun_out/r1_smoke.log; cat gpurun_out/r1_bench.json | cut -c1-300
