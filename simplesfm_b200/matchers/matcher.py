@@ -183,23 +183,15 @@ class Matcher(object):
                 match_table[(a + 1, b + 1)] = host[p, :lens[p]].copy()
         return match_table
 
-    def _simple_matcher(self,
-                        frames: List[Frame],
-                        match_list: np.ndarray) -> Dict[Tuple[int, int], np.array]:
-        """
-        :param frames: Frames with filed descriptors field.
-        :param match_list: List with pairs which must be matched.
-        :return: Dict where the key is a pair from the match_list,
-                and the value is the points that match between images in pair.
-        """
-        match_table = {}
-        for image_id_1, image_id_2 in match_list:
-            matches = self.matcher.match_two_way_cuda(frames[image_id_1 - 1].descriptors,
-                                                      frames[image_id_2 - 1].descriptors).t()
-
-            matches = matches[:, :2].cpu().numpy().astype(np.uint32)
-            match_table[(image_id_1, image_id_2)] = matches
-        return match_table
+    def _simple_matcher(self, frames: List[Frame], match_list: np.ndarray) -> Dict[Tuple[int, int], np.array]:
+        """Mutual nearest-neighbour tables (matcher.py:115-131): per pair the first two rows of
+        `match_two_way_cuda` ([index0, index1, distance]) as an (L, 2) uint32 array."""
+        table = {}
+        nn = self.matcher
+        for a, b in match_list:
+            triple = nn.match_two_way_cuda(frames[a - 1].descriptors, frames[b - 1].descriptors)
+            table[(a, b)] = triple[:2].t().cpu().numpy().astype(np.uint32)
+        return table
 
     def _shard(self, match_list: np.ndarray) -> np.ndarray:
         """Contiguous, chunk-aligned slice of the pair list for this rank (SURVEY.md 8e phase 3).
@@ -212,55 +204,48 @@ class Matcher(object):
         lo, hi = shard_range(len(match_list), bs, dist.get_rank(), dist.get_world_size())
         return match_list[lo:hi]
 
+    @staticmethod
+    def _report(what: str, seconds: float, **counts):
+        logger.info(f'Finished {what}\n Elapsed time: {seconds}\n'
+                    + ''.join(f' {k.replace("_", " ").capitalize()}: {v}\n' for k, v in counts.items()))
+
     def match_frames(self,
                      frames: List[Frame],
                      images_names: dict,
                      match_pairs_filter: callable = None) -> Tuple[List[Frame],
                                                                    Dict[Tuple[int, int], np.array],
                                                                    Dict[int, str]]:
-
+        """Match every id pair of `images_names` that passes `match_pairs_filter`, in the lexicographic order
+        of `itertools.combinations` (matcher.py:133-165).  Returns `(frames, match_table, images_names)`."""
+        t0 = time.time()
         logger.info('Starts matching descriptors.')
-        start = time.time()
-
-        match_list = np.array(list(itertools.combinations(images_names.keys(), r=2)))
-        match_list = np.array(list(filter(match_pairs_filter, match_list))).reshape(-1, 2)
-        local_list = self._shard(match_list)
-
-        match_table = None
-
-        if self.matcher_type == 'simple':
-            match_table = self._simple_matcher(frames, local_list)
-        elif self.matcher_type == 'super_glue':
-            match_table = self._super_glue_matcher(frames, local_list)
-
-        if local_list is not match_list:
+        every = np.array(list(itertools.combinations(images_names.keys(), r=2))).reshape(-1, 2)
+        wanted = every if match_pairs_filter is None else \
+            np.array([p for p in every if match_pairs_filter(p)]).reshape(-1, 2)
+        mine = self._shard(wanted)
+        run = {'simple': self._simple_matcher, 'super_glue': self._super_glue_matcher}.get(self.matcher_type)
+        match_table = run(frames, mine) if run is not None else None
+        if mine is not wanted:      # every rank returns the full, identically ordered table
             from ..distributed import gather_match_tables
-            match_table = gather_match_tables(match_table, match_list)
-
-        num_matched_points = 0
-        for keys, value in match_table.items():
-            num_matched_points += len(value)
-
-        end = time.time()
-        logger.info(f'Finished \n'
-                    f'Elapsed time: {float(end - start)} \n'
-                    f'Num matches: {len(match_list)} \n'
-                    f'Num matched points: {num_matched_points} \n')
-
+            match_table = gather_match_tables(match_table, wanted)
+        self._report('matching', time.time() - t0, num_matches=len(wanted),
+                     num_matched_points=sum(len(v) for v in match_table.values()))
         return frames, match_table, images_names
 
     # ------------------------------------------------------------------------------------------
-    def _extract(self, image: torch.Tensor, mask: torch.Tensor = None) -> Dict[str, torch.Tensor]:
-        data = {'image': image}
-        if mask is not None:
-            data['mask'] = mask
-        return self.super_point_extractor(data)
-
-    def _extract_stream(self, items) -> List[Frame]:
-        """Frames for an iterable of (grey image (H,W) u8 | f32, mask | None) host arrays, in order."""
+    # image sources (matcher.py:167-400).  All three feed one ingestion pipeline (ingest.py): host decode runs ahead
+    # on `decode_threads` threads, pixels go up as they are, SuperPoint runs `extract_batch` images at a time;
+    # image ids are 1-based in arrival order, exactly like the reference's per-image loops.
+    def _frames_from(self, items) -> List[Frame]:
+        """items: iterable of (grey image (H, W) u8 | f32 host array, mask host array | None)."""
         from ..ingest import FrameExtractor
+        t0 = time.time()
+        logger.info('Starts extracting descriptors.')
         ex = FrameExtractor(self.super_point_extractor, self.extract_batch)
-        return [Frame(e.descriptors, e.keypoints, e.scores, e.image) for e in ex.extract(items)]
+        frames = [Frame(e.descriptors, e.keypoints, e.scores, e.image) for e in ex.extract(items)]
+        self._report('extraction', time.time() - t0, num_images=len(frames),
+                     num_keypoints=sum(len(f.keypoints_poses) for f in frames))
+        return frames
 
     def match_datasets(self,
                        datasets,
@@ -269,61 +254,22 @@ class Matcher(object):
                                                                 Dict[Tuple[int, int], np.array],
                                                                 Dict[int, str],
                                                                 List[int]]:
-        """
-        Get ImageFoldersDataset dataset or list of ImageFoldersDatasets and processed all frames from it,
-        image folders type must be set as 'rgb' and 'mask'(if masks are used).  (matcher.py:167-247)
-        """
+        """One `ImageFoldersDataset` or a list of them (folder types 'rgb' and, optionally, 'mask'); the last
+        return value holds, per dataset, the id following its final image (matcher.py:167-247)."""
         from torch.utils.data import DataLoader
+        names, split_index = {}, []
 
-        if match_pairs_filter is None:
-            match_pairs_filter = lambda x: True
+        def samples():
+            for ds in (datasets if isinstance(datasets, list) else [datasets]):
+                for sample in DataLoader(ds, batch_size=1, shuffle=False):
+                    tail = sample['path_rgb'][0].split('/')[-image_name_path_shift:]
+                    names[len(names) + 1] = '_'.join(tail)
+                    grey = sample['rgb'][0, 0].numpy().astype(np.float32, copy=False)
+                    yield grey, ((sample['mask'][0, 0].numpy() > 0) if 'mask' in sample else None)
+                split_index.append(len(names) + 1)
 
-        logger.info('Starts extracting descriptors.')
-        start = time.time()
-        image_bd_index = 1
-        images_bd_index_names = {}
-        processed_frames = []
-        num_keypoints = 0
-
-        if not isinstance(datasets, list):
-            datasets = [datasets]
-
-        dataset_split_bd_index = []
-        if self.extract_batch > 1:
-            def stream():
-                nonlocal image_bd_index
-                for dataset in datasets:
-                    for data in DataLoader(dataset, batch_size=1, shuffle=False):
-                        images_names = '_'.join(data['path_rgb'][0].split('/')[-image_name_path_shift:])
-                        images_bd_index_names[image_bd_index] = images_names
-                        image_bd_index += 1
-                        img = data['rgb'][0, 0].numpy().astype(np.float32, copy=False)
-                        msk = (data['mask'][0, 0].numpy() > 0) if 'mask' in data else None
-                        yield img, msk
-                    dataset_split_bd_index.append(image_bd_index)
-            processed_frames = self._extract_stream(stream())
-            num_keypoints = sum(len(f.keypoints_poses) for f in processed_frames)
-            datasets = []
-        for dataset in datasets:
-            image_dataloader = DataLoader(dataset, batch_size=1, shuffle=False)
-            for data in image_dataloader:
-                images = data['rgb'].to(self.device)
-                images_names = '_'.join(data['path_rgb'][0].split('/')[-image_name_path_shift:])
-                masks = data['mask'].to(self.device) > 0 if 'mask' in data else None
-                result = self._extract(images, masks)
-                processed_frames.append(Frame(result['descriptors'], result['keypoints'], result['scores'], images[0]))
-                images_bd_index_names[image_bd_index] = images_names
-                image_bd_index += 1
-                num_keypoints += len(result['keypoints'])
-            dataset_split_bd_index.append(image_bd_index)
-
-        end = time.time()
-        logger.info(f'Finished \n '
-                    f'Elapsed time: {float(end - start)} \n'
-                    f'Num images: {len(processed_frames)} \n'
-                    f'Num keypoints: {num_keypoints} \n')
-
-        return *self.match_frames(processed_frames, images_bd_index_names, match_pairs_filter), dataset_split_bd_index
+        frames = self._frames_from(samples())
+        return (*self.match_frames(frames, names, match_pairs_filter), split_index)
 
     def match_video_stream(self,
                            vs,
@@ -331,60 +277,24 @@ class Matcher(object):
                            vs_mask=None) -> Tuple[List[Frame],
                                                   Dict[Tuple[int, int], np.array],
                                                   Dict[int, str]]:
-        """
-        Get VideoStreamer and processed all frames from it (matcher.py:249-321).
-        `vs.next_frame()` must return (image float32 (H,W) in [0,1], status, path).
-        """
-        if match_pairs_filter is None:
-            match_pairs_filter = lambda x: True
+        """Every frame of a `VideoStreamer` (`next_frame() -> (f32 image in [0, 1], ok, path)`), optionally with a
+        second streamer delivering the masks; stops at the first failed read of either (matcher.py:249-321)."""
+        names = {}
 
-        logger.info('Starts extracting descriptors.')
-        start = time.time()
-        image_bd_index = 1
-        images_bd_index_names = {}
-        processed_frames = []
-        num_keypoints = 0
-        if self.extract_batch > 1:
-            def stream():
-                nonlocal image_bd_index
-                while True:
-                    image, status, img_path = vs.next_frame()
-                    image_mask = None
-                    if vs_mask is not None:
-                        image_mask, status_mask, img_mask_path = vs_mask.next_frame()
-                        status &= status_mask
-                    if status is False:
-                        return
-                    images_bd_index_names[image_bd_index] = img_path.split('/')[-1]
-                    image_bd_index += 1
-                    yield np.asarray(image, dtype=np.float32), (None if image_mask is None else image_mask > 0)
-            processed_frames = self._extract_stream(stream())
-            num_keypoints = sum(len(f.keypoints_poses) for f in processed_frames)
-        while self.extract_batch <= 1:
-            image, status, img_path = vs.next_frame()
-            if vs_mask is not None:
-                image_mask, status_mask, img_mask_path = vs_mask.next_frame()
-                status &= status_mask
-            if status is False:
-                break
-            image = torch.from_numpy(image)[None, None, :, :].to(self.device)
-            mask = None
-            if vs_mask:
-                mask = torch.from_numpy(image_mask > 0)[None, None, :, :].to(self.device)
-            result = self._extract(image, mask)
-            processed_frames.append(Frame(result['descriptors'], result['keypoints'], result['scores'],
-                                          image.squeeze(1)))
-            images_bd_index_names[image_bd_index] = img_path.split('/')[-1]
-            image_bd_index += 1
-            num_keypoints += len(result['keypoints'])
+        def grabbed():
+            while True:
+                image, ok, path = vs.next_frame()
+                mask = None
+                if vs_mask is not None:
+                    mask, ok_mask, _ = vs_mask.next_frame()
+                    ok = ok and ok_mask
+                if not ok:
+                    return
+                names[len(names) + 1] = path.split('/')[-1]
+                yield np.asarray(image, dtype=np.float32), (None if mask is None else np.asarray(mask) > 0)
 
-        end = time.time()
-        logger.info(f'Finished \n '
-                    f'Elapsed time: {float(end - start)} \n'
-                    f'Num images: {len(processed_frames)} \n'
-                    f'Num keypoints: {num_keypoints} \n')
-
-        return self.match_frames(processed_frames, images_bd_index_names, match_pairs_filter)
+        frames = self._frames_from(grabbed())
+        return self.match_frames(frames, names, match_pairs_filter)
 
     def match_simple_sfm_dataset(self,
                                  dataset_path: str,
@@ -392,63 +302,19 @@ class Matcher(object):
                                  dataset_mask_name: str = None) -> Tuple[List[Frame],
                                                                          Dict[Tuple[int, int], np.array],
                                                                          Dict[int, str]]:
-        """
-        Process every frame listed in `<dataset_path>/views_data.json` (matcher.py:323-400).
-        """
-        from PIL import Image
+        """Every entry of `<dataset_path>/views_data.json['frames']`: `file_path` is the image, the optional key
+        `dataset_mask_name` its mask; both are read as 8-bit grey (PIL mode 'L') (matcher.py:323-400)."""
+        from ..ingest import decode_ahead, load_grey_u8
+        root = Path(dataset_path)
+        with open(root / 'views_data.json', encoding='UTF-8') as fh:
+            entries = json.load(fh)['frames']
 
-        if match_pairs_filter is None:
-            match_pairs_filter = lambda x: True
+        def reader(entry):
+            def read():
+                mask = load_grey_u8(root / entry[dataset_mask_name]) if dataset_mask_name is not None else None
+                return load_grey_u8(root / entry['file_path']), mask     # nonzero grey level == `mask / 255 > 0`
+            return read
 
-        logger.info('Starts extracting descriptors.')
-        start = time.time()
-        image_bd_index = 1
-        images_bd_index_names = {}
-        processed_frames = []
-        num_keypoints = 0
-
-        views_data_json_path = Path(dataset_path, "views_data.json")
-        with open(views_data_json_path, encoding="UTF-8") as file:
-            views_data = json.load(file)
-
-        if self.extract_batch > 1:
-            from ..ingest import decode_ahead, load_grey_u8
-
-            def loader(item):
-                def load():
-                    img = load_grey_u8(Path(dataset_path, item['file_path']))
-                    msk = load_grey_u8(Path(dataset_path, item[dataset_mask_name])) if dataset_mask_name is not None else None
-                    return img, msk          # mask: nonzero grey level == `image_mask / 255 > 0`
-                return load
-
-            frames_meta = views_data['frames']
-            processed_frames = self._extract_stream(decode_ahead([loader(it) for it in frames_meta],
-                                                                 self.decode_threads))
-            for item in frames_meta:
-                images_bd_index_names[image_bd_index] = item['file_path'].split('/')[-1]
-                image_bd_index += 1
-            num_keypoints = sum(len(f.keypoints_poses) for f in processed_frames)
-            views_data = {'frames': []}
-        for item in views_data['frames']:
-            image = np.array(Image.open(Path(dataset_path, item['file_path'])).convert('L')).astype('float32') / 255
-            image_name = item['file_path'].split('/')[-1]
-            mask = None
-            if dataset_mask_name is not None:
-                image_mask = np.array(Image.open(Path(dataset_path, item[dataset_mask_name])).convert('L')
-                                      ).astype('float32') / 255
-                mask = torch.from_numpy(image_mask > 0)[None, None, :, :].to(self.device)
-            image = torch.from_numpy(image)[None, None, :, :].to(self.device)
-            result = self._extract(image, mask)
-            processed_frames.append(Frame(result['descriptors'], result['keypoints'], result['scores'],
-                                          image.squeeze(1)))
-            images_bd_index_names[image_bd_index] = image_name
-            image_bd_index += 1
-            num_keypoints += len(result['keypoints'])
-
-        end = time.time()
-        logger.info(f'Finished \n '
-                    f'Elapsed time: {float(end - start)} \n'
-                    f'Num images: {len(processed_frames)} \n'
-                    f'Num keypoints: {num_keypoints} \n')
-
-        return self.match_frames(processed_frames, images_bd_index_names, match_pairs_filter)
+        names = {i + 1: e['file_path'].split('/')[-1] for i, e in enumerate(entries)}
+        frames = self._frames_from(decode_ahead([reader(e) for e in entries], self.decode_threads))
+        return self.match_frames(frames, names, match_pairs_filter)
