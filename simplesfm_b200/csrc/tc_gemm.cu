@@ -77,7 +77,11 @@ __device__ __forceinline__ uint32_t bn_relu_pair(uint32_t x, float a0, float b0,
 // normalised hidden activations never make a round trip through HBM.
 // RMW = true compiles the epilogue for the coalesced residual update only (out_f += result), which keeps its
 // prefetched fp32 values in registers across tiles.
-template <int BN, int KBLOCKS, bool XF, bool RMW>
+// CG2 = true runs the kernel on CTA pairs (cluster of 2, tcgen05 cta_group::2): one MMA covers 256 rows x BN
+// columns, rows split between the two CTAs' A tiles / TMEM, and each CTA keeps only HALF of the [BN x K] weight
+// panel (its half of N) in shared memory.  Per flop the tensor pipe reads half as many B bytes from shared memory
+// and the activations are re-read from L2 once per 256 instead of once per 128 output columns.
+template <int BN, int KBLOCKS, bool XF, bool RMW, bool CG2>
 __global__ void __launch_bounds__(XF ? GEMM_THREADS + 128 : GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO, TcGemm p) {
@@ -85,7 +89,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   // carve: [W panel: KBLOCKS * BN * 128][A ring: STAGES * 16 KB][2 output slabs][bias][barriers]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
-  uint8_t* sA = smem + KBLOCKS * BN * 128;
+  constexpr int BNL = CG2 ? BN / 2 : BN;   // weight-panel rows held by this CTA
+  uint8_t* sA = smem + KBLOCKS * BNL * 128;
   uint8_t* sO = sA + STAGES * A_STAGE_BYTES;
   float* sBias = reinterpret_cast<float*>(sO + 2 * SLAB_BYTES);
   Barriers* bars = reinterpret_cast<Barriers*>(sBias + BN);
@@ -115,11 +120,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(&bars->acc_full[b], 1);
-      mbar_init(&bars->acc_empty[b], 8);
+      mbar_init(&bars->acc_empty[b], CG2 ? 16 : 8);   // CG2: the peer's epilogue warps arrive on the leader's barrier
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  const int rank = CG2 ? (int)cluster_ctarank() : 0;
+  if (CG2) cluster_sync_all();   // both CTAs' barriers are initialised before anything can arrive on them
+  if (warp == 1) {
+    if (CG2) tmem_alloc_pair<TMEM_COLS>(&bars->tmem_base); else tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -127,8 +136,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   // work decomposition: slot -> panel jobs (batch, panel); sub -> m tiles of that job
   const int n_pj = p.batch * p.num_panels;
-  const int slot = blockIdx.x / p.cpp, sub = blockIdx.x % p.cpp;
-  const int n_slots = gridDim.x / p.cpp;
+  const int unit = CG2 ? blockIdx.x / 2 : blockIdx.x;          // CTA (pair) index
+  const int n_units = CG2 ? gridDim.x / 2 : gridDim.x;
+  const int slot = unit / p.cpp, sub = unit % p.cpp;
+  const int n_slots = n_units / p.cpp;
   const int k1_blocks = p.K1 / BK;
 
   if (warp == 0) {
@@ -143,10 +154,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(&bars->w_empty, wphase);
           wphase ^= 1;
         }
-        mbar_arrive_expect_tx(&bars->w_full, KBLOCKS * BN * 128);
-        const int wrow = p.w_row_base + b * p.w_row_stride + panel * BN;
-        for (int kb = 0; kb < KBLOCKS; kb++) tma_load_2d(sW + kb * BN * 128, &mapW, &bars->w_full, kb * BK, wrow);
-        for (int mt = sub; mt < p.num_m_tiles; mt += p.cpp) {
+        // CG2: only the leader's barriers collect transaction bytes (of both CTAs' loads)
+        if (!CG2 || rank == 0) mbar_arrive_expect_tx(&bars->w_full, (CG2 ? 2 : 1) * KBLOCKS * BNL * 128);
+        const int wrow = p.w_row_base + b * p.w_row_stride + panel * BN + rank * BNL;
+        for (int kb = 0; kb < KBLOCKS; kb++) {
+          if (CG2) tma_load_2d_pair(sW + kb * BNL * 128, &mapW, &bars->w_full, kb * BK, wrow);
+          else tma_load_2d(sW + kb * BNL * 128, &mapW, &bars->w_full, kb * BK, wrow);
+        }
+        for (int pt = sub; pt < p.num_m_tiles; pt += p.cpp) {
+          const int mt = CG2 ? 2 * pt + rank : pt;   // this CTA's 128-row tile
           const int arow = b * p.a_row_stride + mt * BM;
           if ((p.l2_prefetch & 1) && mt + p.cpp < p.num_m_tiles) {
             const int nrow = arow + p.cpp * BM;
@@ -159,11 +175,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           for (int kb = 0; kb < KBLOCKS; kb++) {
             DBG_WAIT(0, mbar_wait(&bars->a_empty[stage], phase ^ 1));
-            mbar_arrive_expect_tx(&bars->a_full[stage], A_STAGE_BYTES);
-            if (kb < k1_blocks)
-              tma_load_2d(sA + stage * A_STAGE_BYTES, &mapA, &bars->a_full[stage], kb * BK, arow);
-            else
-              tma_load_2d(sA + stage * A_STAGE_BYTES, &mapA2, &bars->a_full[stage], (kb - k1_blocks) * BK, arow);
+            if (!CG2 || rank == 0) mbar_arrive_expect_tx(&bars->a_full[stage], (CG2 ? 2 : 1) * A_STAGE_BYTES);
+            const CUtensorMap* am = kb < k1_blocks ? &mapA : &mapA2;
+            const int ax = (kb < k1_blocks ? kb : kb - k1_blocks) * BK;
+            if (CG2) tma_load_2d_pair(sA + stage * A_STAGE_BYTES, am, &bars->a_full[stage], ax, arow);
+            else tma_load_2d(sA + stage * A_STAGE_BYTES, am, &bars->a_full[stage], ax, arow);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -174,19 +190,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0);
+    if (lane == 0 && rank == 0) {   // CG2: the leader issues for the pair
+      constexpr uint32_t idesc = umma_idesc_bf16(CG2 ? 2 * BM : BM, BN, 0);
       int stage = 0, phase = 0, wphase = 0, tile = 0;
       // descriptors of every A stage / W k-block are loop invariants: build them once
       uint64_t w_desc[KBLOCKS];
       const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA), 16, 1024);  // stage s: + s * A_STAGE_BYTES
 #pragma unroll
-      for (int kb = 0; kb < KBLOCKS; kb++) w_desc[kb] = umma_desc_sw128(smem_u32(sW + kb * BN * 128), 16, 1024);
+      for (int kb = 0; kb < KBLOCKS; kb++) w_desc[kb] = umma_desc_sw128(smem_u32(sW + kb * BNL * 128), 16, 1024);
       for (int pj = slot; pj < n_pj; pj += n_slots) {
         mbar_wait(&bars->w_full, wphase);
         wphase ^= 1;
         tc_fence_after();
-        for (int mt = sub; mt < p.num_m_tiles; mt += p.cpp, tile++) {
+        for (int pt = sub; pt < p.num_m_tiles; pt += p.cpp, tile++) {
           const int buf = tile & 1;
           DBG_WAIT(1, mbar_wait(&bars->acc_empty[buf], ((tile >> 1) & 1) ^ 1));
           tc_fence_after();
@@ -198,16 +214,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const uint64_t ad = umma_desc_advance(a_desc0, stage * A_STAGE_BYTES), bd = w_desc[kb];
 #pragma unroll
             for (int k = 0; k < BK / 16; k++)
-              umma_ss(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, (kb | k) != 0);
-            umma_commit(&bars->a_empty[stage]);
+            {
+              if (CG2) umma_ss_pair(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, (kb | k) != 0);
+              else umma_ss(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, (kb | k) != 0);
+            }
+            if (CG2) umma_commit_pair(&bars->a_empty[stage]); else umma_commit(&bars->a_empty[stage]);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          umma_commit(&bars->acc_full[buf]);
+          if (CG2) umma_commit_pair(&bars->acc_full[buf]); else umma_commit(&bars->acc_full[buf]);
         }
-        umma_commit(&bars->w_empty);
+        if (CG2) umma_commit_pair(&bars->w_empty); else umma_commit(&bars->w_empty);
       }
     }
   } else if (XF && warp >= 10) {
@@ -303,7 +322,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         sBias[i] = (p.bias != nullptr && n < p.N) ? p.bias[n] : 0.f;
       }
       named_bar_sync(1, 256);
-      for (int mt = sub; mt < p.num_m_tiles; mt += p.cpp, tile++) {
+      for (int pt = sub; pt < p.num_m_tiles; pt += p.cpp, tile++) {
+        const int mt = CG2 ? 2 * pt + rank : pt;   // this CTA's 128-row tile
         const int buf = tile & 1;
         if constexpr (RMW) {
           // ---- residual update X += delta (fp32 master + bf16 shadow).  The accumulator chunk goes through a
@@ -485,7 +505,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+        if (lane == 0) {
+          if (CG2) mbar_arrive_leader(&bars->acc_empty[buf]); else mbar_arrive(&bars->acc_empty[buf]);
+        }
         }  // !RMW
       }
     }
@@ -497,15 +519,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (CG2) cluster_sync_all();   // no remote arrive / pair-wide MMA may still target a CTA that has left
+  if (warp == 1) {
+    if (CG2) tmem_dealloc_pair<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
 }
 
-template <int BN, int KBLOCKS, bool XF = false, bool RMW = false>
+template <int BN, int KBLOCKS, bool XF = false, bool RMW = false, bool CG2 = false>
 int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mW,
-           const CUtensorMap& mO, int num_sms, cudaStream_t st) {
+           const CUtensorMap& mO, int num_sms_in, cudaStream_t st) {
   TcGemm p = p_in;
+  const int num_sms = CG2 ? num_sms_in / 2 : num_sms_in;   // CG2: work is dealt to CTA pairs
   p.num_panels = cdiv(p.N, BN);
-  p.num_m_tiles = cdiv(p.M, BM);
+  p.num_m_tiles = cdiv(p.M, CG2 ? 2 * BM : BM);
   const int n_pj = p.batch * p.num_panels;
   int cpp = num_sms / n_pj;
   if (cpp < 1) cpp = 1;
@@ -513,11 +539,12 @@ int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, co
   int n_slots = num_sms / cpp;
   if (n_slots > n_pj) n_slots = n_pj;
   p.cpp = cpp;
-  const size_t smem = (size_t)KBLOCKS * BN * 128 + STAGES * A_STAGE_BYTES + 2 * SLAB_BYTES + BN * sizeof(float) +
-                      sizeof(Barriers) + 1024;
+  const size_t smem = (size_t)KBLOCKS * (CG2 ? BN / 2 : BN) * 128 + STAGES * A_STAGE_BYTES + 2 * SLAB_BYTES +
+                      BN * sizeof(float) + sizeof(Barriers) + 1024;
   static bool configured = false;
   if (!configured) {
-    SFM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, KBLOCKS, XF, RMW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SFM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, KBLOCKS, XF, RMW, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
     configured = true;
   }
   static long long* dbg = nullptr;
@@ -527,7 +554,23 @@ int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, co
   p.dbg_flags = getenv("SFM_TC_FLAGS") ? atoi(getenv("SFM_TC_FLAGS")) : 0;
   p.l2_prefetch = getenv("SFM_TC_PREFETCH") ? atoi(getenv("SFM_TC_PREFETCH")) : 2;   // bit 0: A tiles, bit 1: residual
   if (want_dbg) cudaMemsetAsync(dbg, 0, 148 * 3 * 6 * sizeof(long long), st);
-  tc_gemm_kernel<BN, KBLOCKS, XF, RMW><<<n_slots * cpp, XF ? GEMM_THREADS + 128 : GEMM_THREADS, smem, st>>>(mA, mA2, mW, mO, p);
+  if (CG2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * n_slots * cpp);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SFM_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, KBLOCKS, XF, RMW, CG2>, mA, mA2, mW, mO, p));
+  } else {
+    tc_gemm_kernel<BN, KBLOCKS, XF, RMW, CG2><<<n_slots * cpp, XF ? GEMM_THREADS + 128 : GEMM_THREADS, smem, st>>>(mA, mA2, mW, mO, p);
+  }
   SFM_LAUNCH_CHECK();
   if (want_dbg) {
     static long long host[148 * 3 * 6];
@@ -604,7 +647,12 @@ int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
   else
     mA2 = mA;
   const bool wide = (p.K <= 256) && (p.N > 128);
-  SFM_TRY(make_tmap_bf16(&mW, p.W, p.w_rows, p.K, p.ldw, wide ? 256 : 128));
+  // CTA-pair kernel: plain bf16-output GEMMs whose rows / columns are whole 256-wide pair tiles
+  static const int cg2_env = getenv("SFM_TC_CG2") ? atoi(getenv("SFM_TC_CG2")) : 1;
+  const bool accum_any = p.accumulate_f != 0 || p.out_f != nullptr;
+  const bool cg2 = cg2_env && !accum_any && p.xf_scale == nullptr && p.out_h != nullptr && p.batch == 1 &&
+                   p.M % 256 == 0 && p.N % 256 == 0 && (p.K == 256 || p.K == 512) && num_sms % 2 == 0;
+  SFM_TRY(make_tmap_bf16(&mW, p.W, p.w_rows, p.K, p.ldw, (wide && !cg2) ? 256 : 128));
   // output map: rows beyond M and columns beyond N are clipped by the TMA unit
   if (p.out_h != nullptr)
     SFM_TRY(make_tmap_bf16(&mO, p.out_h, p.M, p.N, p.out_h_ld, 128));
@@ -617,6 +665,10 @@ int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
                     (p.out_h == nullptr || p.out_h_ld % 4 == 0);
   const bool rmw = q.coalesced_rmw != 0;
   SFM_REQUIRE(p.xf_scale == nullptr || rmw, "tc_gemm: fused BatchNorm apply is only built for the residual-update epilogue");
+  if (cg2) {
+    if (p.K == 256) return launch<256, 4, false, false, true>(q, mA, mA2, mW, mO, num_sms, st);
+    return launch<256, 8, false, false, true>(q, mA, mA2, mW, mO, num_sms, st);
+  }
   if (p.K == 128) {
     q.coalesced_rmw = 0;   // K = 128 shapes never carry the residual stream: generic epilogue
     if (wide) return launch<256, 2>(q, mA, mA2, mW, mO, num_sms, st);

@@ -134,6 +134,9 @@ class Matcher(object):
         P = len(pairs0)
         L = lib()
         super_chunk = max(bs, super_chunk // bs * bs)
+        # chunks per launch: bounded so that one launch holds at most 256 pairs (score matrices + activations of a
+        # launch at 4096 keypoints stay around 35 GB)
+        fuse_limit = max(1, min(self.fuse_chunks, 256 // bs))
         for s0 in range(0, P, super_chunk):
             s1 = min(P, s0 + super_chunk)
             n_sc = s1 - s0
@@ -151,7 +154,7 @@ class Matcher(object):
                     raise RuntimeError("stack expects each tensor to be equal size (images of one chunk differ)")
                 key = (k0, k1, next(iter(hw0)), next(iter(hw1)))
                 full = (c1 - c0) == bs
-                if (plan and full and tuple(plan[-1][2:6]) == key and plan[-1][6] < self.fuse_chunks
+                if (plan and full and tuple(plan[-1][2:6]) == key and plan[-1][6] < fuse_limit
                         and plan[-1][1] == plan[-1][6] * bs):
                     plan[-1][1] += bs
                     plan[-1][6] += 1

@@ -57,6 +57,28 @@ def test_tc_gemm(handle, dev, M, N, K, K1):
         torch.testing.assert_close(out_h.float(), ref2, rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("M,N,K,K1", [(256, 256, 256, 256), (1024, 768, 256, 256), (2048, 512, 512, 256),
+                                      (768, 256, 512, 512), (512, 512, 512, 512)])
+def test_tc_gemm_cta_pair(handle, dev, M, N, K, K1):
+    """bf16-output GEMMs whose rows and columns are whole 256-wide tiles run on CTA pairs (cluster of 2,
+    tcgen05 cta_group::2: pair-wide MMA, half of the weight panel per CTA, barriers on the leader CTA)."""
+    from simplesfm_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(M * 3 + N)
+    A = torch.randn(M, K, generator=g).to(dev).bfloat16()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(dev)
+    A1 = A[:, :K1].contiguous()
+    A2 = A[:, K1:].contiguous() if K1 < K else None
+    out_h = torch.zeros(M, N, dtype=torch.bfloat16, device=dev)
+    for relu in (0, 1):
+        _lib.check(_lib.lib().sfm_tc_gemm(handle.h, A1.data_ptr(), None if A2 is None else A2.data_ptr(), W.data_ptr(),
+                                          M, N, K, K1, bias.data_ptr(), 0.5, relu, out_h.data_ptr(), None, 0, _stream()))
+        ref = 0.5 * (A.float() @ W.float().t()) + bias
+        if relu:
+            ref = torch.relu(ref)
+        torch.testing.assert_close(out_h.float(), ref, rtol=2e-2, atol=2e-2)
+
+
 @pytest.mark.parametrize("B,N0,N1,cross", [(1, 256, 256, False), (2, 512, 384, True), (3, 333, 251, True),
                                            (3, 333, 251, False), (1, 2048, 2048, True), (2, 100, 60, True)])
 def test_tc_attention(handle, dev, B, N0, N1, cross):
