@@ -8,12 +8,12 @@ python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_o
 python bench.py > gpurun_out/r1_bench.json 2> gpurun_out/r1_bench.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r1_bench_reference.json 2> gpurun_out/r1_bench_reference.err; echo "reference rc=$?"
 # launch list of one bench step (warm-up launches are skipped by count below when summarising)
-python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/plain_bench.log 2>&1 && \
+python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/plain_bench.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv --log-file gpurun_out/r1_launches_bench.csv \
-      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "launch list rc=$?"
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "launch list rc=$?"
 # full captures: one GNN layer's kernels + Sinkhorn of a 40-pair forward, and SuperPoint bf16 on 4 images
 python tools/prof_forward.py 40 2048 1 > gpurun_out/plain_fwd.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on --launch-skip 60 -c 14 -o gpurun_out/r1_superglue_kernels -f \
+  ncu --set full --clock-control none --import-source on --launch-skip 60 -c 7 -o gpurun_out/r1_superglue_kernels -f \
       python tools/prof_forward.py 40 2048 1 > gpurun_out/ncu_sg.log 2>&1; echo "sg full rc=$?"
 python tools/prof_forward.py 40 2048 1 > /dev/null 2>&1 && \
   ncu --set full --clock-control none -k regex:sks_ -c 3 -o gpurun_out/r1_sinkhorn_kernels -f \
