@@ -116,7 +116,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&bars->a_full[s], 1);
       mbar_init(&bars->a_empty[s], 1);
-      mbar_init(&bars->a_ready[s], 4);
+      mbar_init(&bars->a_ready[s], CG2 ? 8 : 4);   // CG2: the peer's transform warps arrive on the leader's barrier
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(&bars->acc_full[b], 1);
@@ -164,7 +164,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int pt = sub; pt < p.num_m_tiles; pt += p.cpp) {
           const int mt = CG2 ? 2 * pt + rank : pt;   // this CTA's 128-row tile
           const int arow = b * p.a_row_stride + mt * BM;
-          if ((p.l2_prefetch & 1) && mt + p.cpp < p.num_m_tiles) {
+          if ((p.l2_prefetch & 1) && pt + p.cpp < p.num_m_tiles) {
             const int nrow = arow + p.cpp * BM;
             for (int kb = 0; kb < KBLOCKS; kb++) {
               if (kb < k1_blocks)
@@ -175,10 +175,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           for (int kb = 0; kb < KBLOCKS; kb++) {
             DBG_WAIT(0, mbar_wait(&bars->a_empty[stage], phase ^ 1));
-            if (!CG2 || rank == 0) mbar_arrive_expect_tx(&bars->a_full[stage], (CG2 ? 2 : 1) * A_STAGE_BYTES);
+            // CG2 without XF: both CTAs' A bytes are credited to the leader's barrier (the MMA waits there);
+            // with XF each CTA's own transform warps wait for its own tile first
+            constexpr bool PAIR_A = CG2 && !XF;
+            if (!PAIR_A || rank == 0) mbar_arrive_expect_tx(&bars->a_full[stage], (PAIR_A ? 2 : 1) * A_STAGE_BYTES);
             const CUtensorMap* am = kb < k1_blocks ? &mapA : &mapA2;
             const int ax = (kb < k1_blocks ? kb : kb - k1_blocks) * BK;
-            if (CG2) tma_load_2d_pair(sA + stage * A_STAGE_BYTES, am, &bars->a_full[stage], ax, arow);
+            if (PAIR_A) tma_load_2d_pair(sA + stage * A_STAGE_BYTES, am, &bars->a_full[stage], ax, arow);
             else tma_load_2d(sA + stage * A_STAGE_BYTES, am, &bars->a_full[stage], ax, arow);
             if (++stage == STAGES) {
               stage = 0;
@@ -248,7 +251,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     bool first = true;
     for (int pj = slot; pj < n_pj; pj += n_slots) {
       const int b = pj / p.num_panels;
-      for (int mt = sub; mt < p.num_m_tiles; mt += p.cpp) {
+      for (int pt = sub; pt < p.num_m_tiles; pt += p.cpp) {
+        const int mt = CG2 ? 2 * pt + rank : pt;   // this CTA's 128-row tile
         const float4 *sc, *sh;
         group_ptr(b, mt, sc, sh);
         if (first) {
@@ -265,10 +269,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             int nkb = kb + 1;
             if (nkb == KBLOCKS) {
               nkb = 0;
-              if (mt + p.cpp < p.num_m_tiles)
-                group_ptr(b, mt + p.cpp, nsc, nsh);
+              if (pt + p.cpp < p.num_m_tiles)
+                group_ptr(b, mt + (CG2 ? 2 : 1) * p.cpp, nsc, nsh);
               else if (pj + n_slots < n_pj)
-                group_ptr((pj + n_slots) / p.num_panels, sub, nsc, nsh);
+                group_ptr((pj + n_slots) / p.num_panels, CG2 ? 2 * sub + rank : sub, nsc, nsh);
               // else: last stage of this CTA, the (unused) prefetch re-reads the current group
             }
             na0 = __ldg(nsc + nkb * 16 + j * 2); na1 = __ldg(nsc + nkb * 16 + j * 2 + 1);
@@ -293,7 +297,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->a_ready[stage]);
+          if (lane == 0) {
+            if (CG2) mbar_arrive_leader(&bars->a_ready[stage]); else mbar_arrive(&bars->a_ready[stage]);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -342,9 +348,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               dst[it] = r < p.M ? *reinterpret_cast<const float4*>(src + r * p.out_f_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           };
-          if ((p.l2_prefetch & 2) && mt + p.cpp < p.num_m_tiles && ch == 0) {
+          const bool has_next = pt + p.cpp < p.num_m_tiles;
+          const int mt_next = mt + (CG2 ? 2 : 1) * p.cpp;
+          if ((p.l2_prefetch & 2) && has_next && ch == 0) {
             // and the tile after that is pulled into L2 (a prefetch holds no registers)
-            const long long nrow0 = (long long)(mt + p.cpp) * BM + rsub;
+            const long long nrow0 = (long long)mt_next * BM + rsub;
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
               const int n0 = panel * BN + wg * HALF + c * 32;
@@ -383,8 +391,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             named_bar_sync(2 + wg, 128);
             if (c + 1 < NCH) {
               load_old(mt, c + 1, oldb[(c + 1) & 1]);
-            } else if (mt + p.cpp < p.num_m_tiles) {
-              load_old(mt + p.cpp, 0, oldb[0]);
+            } else if (has_next) {
+              load_old(mt_next, 0, oldb[0]);
               have_old = true;
             } else {
               have_old = false;
@@ -405,7 +413,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+          if (lane == 0) {
+            if (CG2) mbar_arrive_leader(&bars->acc_empty[buf]); else mbar_arrive(&bars->acc_empty[buf]);
+          }
         } else {
         DBG_WAIT(0, mbar_wait(&bars->acc_full[buf], (tile >> 1) & 1));
         tc_fence_after();
@@ -557,7 +567,7 @@ int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, co
   if (CG2) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * n_slots * cpp);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(XF ? GEMM_THREADS + 128 : GEMM_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -652,7 +662,10 @@ int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
   const bool accum_any = p.accumulate_f != 0 || p.out_f != nullptr;
   const bool cg2 = cg2_env && !accum_any && p.xf_scale == nullptr && p.out_h != nullptr && p.batch == 1 &&
                    p.M % 256 == 0 && p.N % 256 == 0 && (p.K == 256 || p.K == 512) && num_sms % 2 == 0;
-  SFM_TRY(make_tmap_bf16(&mW, p.W, p.w_rows, p.K, p.ldw, (wide && !cg2) ? 256 : 128));
+  static const int cg2x_on = getenv("SFM_TC_CG2X") ? atoi(getenv("SFM_TC_CG2X")) : 1;
+  const bool cg2x = cg2x_on && p.xf_scale != nullptr && p.accumulate_f && p.batch == 1 && p.M % 256 == 0 &&
+                    p.N % 128 == 0 && p.K == 512 && num_sms % 2 == 0;
+  SFM_TRY(make_tmap_bf16(&mW, p.W, p.w_rows, p.K, p.ldw, cg2x ? 64 : ((wide && !cg2) ? 256 : 128)));
   // output map: rows beyond M and columns beyond N are clipped by the TMA unit
   if (p.out_h != nullptr)
     SFM_TRY(make_tmap_bf16(&mO, p.out_h, p.M, p.N, p.out_h_ld, 128));
@@ -680,7 +693,11 @@ int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
     return rmw ? launch<128, 4, false, true>(q, mA, mA2, mW, mO, num_sms, st)
                : launch<128, 4>(q, mA, mA2, mW, mO, num_sms, st);
   }
-  if (p.xf_scale != nullptr) return launch<128, 8, true, true>(q, mA, mA2, mW, mO, num_sms, st);
+  if (p.xf_scale != nullptr) {
+    // residual update with fused BatchNorm apply: CTA pairs (256 x 128 pair tiles, 64 weight rows per CTA)
+    if (cg2x) return launch<128, 8, true, true, true>(q, mA, mA2, mW, mO, num_sms, st);
+    return launch<128, 8, true, true>(q, mA, mA2, mW, mO, num_sms, st);
+  }
   return rmw ? launch<128, 8, false, true>(q, mA, mA2, mW, mO, num_sms, st)
              : launch<128, 8>(q, mA, mA2, mW, mO, num_sms, st);
 }
