@@ -662,7 +662,7 @@ int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
   const bool accum_any = p.accumulate_f != 0 || p.out_f != nullptr;
   const bool cg2 = cg2_env && !accum_any && p.xf_scale == nullptr && p.out_h != nullptr && p.batch == 1 &&
                    p.M % 256 == 0 && p.N % 256 == 0 && (p.K == 256 || p.K == 512) && num_sms % 2 == 0;
-  static const int cg2x_on = getenv("SFM_TC_CG2X") ? atoi(getenv("SFM_TC_CG2X")) : 1;
+  static const int cg2x_on = getenv("SFM_TC_CG2X") ? atoi(getenv("SFM_TC_CG2X")) : 0;   // measured neutral: opt-in
   const bool cg2x = cg2x_on && p.xf_scale != nullptr && p.accumulate_f && p.batch == 1 && p.M % 256 == 0 &&
                     p.N % 128 == 0 && p.K == 512 && num_sms % 2 == 0;
   SFM_TRY(make_tmap_bf16(&mW, p.W, p.w_rows, p.K, p.ldw, cg2x ? 64 : ((wide && !cg2) ? 256 : 128)));
