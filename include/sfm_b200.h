@@ -159,6 +159,13 @@ SFM_API int sfm_sinkhorn_match(const float* scores, int B, int N, int M, float a
 SFM_API int sfm_sinkhorn_match_scaled(float* scores, int B, int N, int M, float alpha, int iters, float match_threshold,
                                       int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
                                       void* workspace, size_t workspace_bytes, void* stream);
+/* Same, with the iterations running on a packed fp16 copy of the kernel matrix (BASELINE config 5 "16-bit
+ * storage"): half the HBM bytes per sweep, `scores` is NOT modified, the final arg-max passes use the fp32 scores. */
+SFM_API size_t sfm_sinkhorn_half_workspace_bytes(int B, int N, int M);
+SFM_API int sfm_sinkhorn_match_scaled_half(const float* scores, int B, int N, int M, float alpha, int iters,
+                                           float match_threshold, int64_t* matches0, int64_t* matches1,
+                                           float* mscores0, float* mscores1, void* workspace, size_t workspace_bytes,
+                                           void* stream);
 
 /* ---- kernel-level hooks of the bf16 tcgen05 path (tests/, bench) ---------------------------------
  * sfm_tc_gemm: out[M,N] = alpha * [A | A2][M,K] * W[N,K]^T + bias (bf16 operands, K in {256,512},

@@ -65,6 +65,10 @@ _SIGNATURES = {
     "sfm_sinkhorn_match": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                      C.c_void_p]),
+    "sfm_sinkhorn_half_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
+    "sfm_sinkhorn_match_scaled_half": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                 C.c_void_p]),
     "sfm_sinkhorn_match_scaled": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                             C.c_void_p]),

@@ -478,6 +478,38 @@ int sfm_sinkhorn_match(const float* scores, int B, int N, int M, float alpha, in
                         mscores0, mscores1, (cudaStream_t)stream);
 }
 
+size_t sfm_sinkhorn_half_workspace_bytes(int B, int N, int M) {
+  if (B < 0 || N <= 0 || M <= 0) return 0;
+  return sfm_sinkhorn_workspace_bytes(B, N, M) + align_up((size_t)B * N * M * 2, 256);
+}
+
+int sfm_sinkhorn_match_scaled_half(const float* scores, int B, int N, int M, float alpha, int iters,
+                                   float match_threshold, int64_t* matches0, int64_t* matches1, float* mscores0,
+                                   float* mscores1, void* ws, size_t ws_bytes, void* stream) {
+  SFM_REQUIRE(matches0 && matches1 && mscores0 && mscores1 && scores, "sfm_sinkhorn_match_scaled_half: NULL argument");
+  SFM_REQUIRE(M % 4 == 0 && M <= 4096 && iters > 0 && B >= 0 && N > 0,
+              "sfm_sinkhorn_match_scaled_half: needs M %% 4 == 0, M <= 4096, iters > 0");
+  const size_t base = sfm_sinkhorn_workspace_bytes(B, N, M);
+  SFM_REQUIRE(ws_bytes >= sfm_sinkhorn_half_workspace_bytes(B, N, M), "sfm_sinkhorn_match_scaled_half: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena a(ws, base);
+  OtBuffers b;
+  ot_carve(a, B, N, M, b);
+  SFM_CUDA(cudaMemsetAsync(b.counters, 0, sinkhorn_counter_ints(B, M) * sizeof(int), st));
+  SinkhornArgs s;
+  s.S = scores; s.B = B; s.N = N; s.M = M; s.alpha = alpha; s.iters = iters;
+  s.u = b.u; s.v = b.v; s.part = b.part; s.counters = b.counters; s.R = b.R;
+  s.fast = true;
+  s.fused_part = b.fused;
+  s.kb = b.kb;
+  s.col_idx = b.idx1;
+  s.rowmax = b.max0;                                                   // scores stay intact
+  s.k16 = reinterpret_cast<__half*>(static_cast<char*>(ws) + base);    // the iterations stream this copy
+  SFM_TRY(sinkhorn_run(s, st));
+  return sinkhorn_match(s, match_threshold, b.max0, b.idx0, b.max1, b.idx1, (long long*)matches0, (long long*)matches1,
+                        mscores0, mscores1, st);
+}
+
 int sfm_sinkhorn_match_scaled(float* scores, int B, int N, int M, float alpha, int iters, float match_threshold,
                               int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1, void* ws,
                               size_t ws_bytes, void* stream) {

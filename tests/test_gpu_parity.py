@@ -404,3 +404,33 @@ def test_matcher_edge_cases(sp_weights, sg_weights, dev):
     assert table == {}
     _, table, _ = m.match_frames(frames[:1], {1: "0"}, None)
     assert table == {}
+
+
+def test_sinkhorn_match_scaled_half_storage(dev):
+    """Stand-alone Sinkhorn + mutual matching with the iterations on a packed fp16 copy of the kernel matrix
+    (BASELINE config 5, 16-bit storage): scores untouched, matches equal to the exact log-space path."""
+    from simplesfm_b200 import _lib
+    L = _lib.lib()
+    B, N, M = 3, 200, 328
+    g = torch.Generator().manual_seed(11)
+    S = torch.randn(B, N, M, generator=g) * 2.0
+    for b in range(B):
+        S[b, torch.arange(100), torch.randperm(M, generator=g)[:100]] += 12.0
+    Sd = S.to(dev)
+    keep = Sd.clone()
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for fn, wsb in ((L.sfm_sinkhorn_match, L.sfm_sinkhorn_workspace_bytes(B, N, M)),
+                    (L.sfm_sinkhorn_match_scaled_half, L.sfm_sinkhorn_half_workspace_bytes(B, N, M))):
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        m0 = torch.empty(B, N, dtype=torch.int64, device=dev)
+        m1 = torch.empty(B, M, dtype=torch.int64, device=dev)
+        s0, s1 = torch.empty(B, N, device=dev), torch.empty(B, M, device=dev)
+        _lib.check(fn(Sd.data_ptr(), B, N, M, 1.0, 50, 0.2, m0.data_ptr(), m1.data_ptr(), s0.data_ptr(), s1.data_ptr(),
+                      ws.data_ptr(), ws.numel(), st))
+        outs.append((m0.cpu(), m1.cpu(), s0.cpu()))
+    assert torch.equal(Sd, keep)                       # scores not modified
+    (a0, a1, sa), (b0, b1, sb) = outs
+    assert int((a0 > -1).sum()) >= 250
+    assert torch.equal(a0, b0) and torch.equal(a1, b1)
+    close(sb, sa, 2e-3, 1e-4)
