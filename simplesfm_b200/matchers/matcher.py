@@ -13,7 +13,6 @@ match tables come back with a single device->host copy per super-chunk.
 """
 __all__ = ['Matcher']
 
-import itertools
 import json
 import logging
 import time
@@ -208,6 +207,33 @@ class Matcher(object):
         return match_list[lo:hi]
 
     @staticmethod
+    def pair_list(ids, match_pairs_filter: callable = None) -> np.ndarray:
+        """(P, 2) array of the id pairs to match: `itertools.combinations(ids, 2)` order, filtered
+        (matcher.py:143-144).  Built without a Python loop over the pairs where possible (scenes with 10^5..10^6
+        pairs): the upper triangle comes from `np.triu_indices`, and a filter written with array
+        arithmetic -- e.g. the reference's `lambda x: np.abs(x[0] - x[1]) < radius`
+        (scripts/generate_simple_sfm_dataset_from_scene.py:140-143) -- is evaluated once on all pairs; its answer is
+        used only if it is a boolean vector that agrees with pair-by-pair evaluation on a sample, otherwise the
+        filter is applied pair by pair like the reference does."""
+        ids = np.asarray(list(ids))
+        a, b = np.triu_indices(len(ids), k=1)
+        every = np.stack([ids[a], ids[b]], axis=1).reshape(-1, 2)
+        if match_pairs_filter is None or len(every) == 0:
+            return every
+        keep = None
+        try:
+            ans = match_pairs_filter(every.T)
+            if isinstance(ans, np.ndarray) and ans.dtype == np.bool_ and ans.shape == (len(every),):
+                probe = np.unique(np.linspace(0, len(every) - 1, num=min(len(every), 32)).astype(np.int64))
+                if all(bool(match_pairs_filter(every[i])) == bool(ans[i]) for i in probe):
+                    keep = ans
+        except Exception:       # not an array-style filter
+            keep = None
+        if keep is None:
+            keep = np.fromiter((bool(match_pairs_filter(p)) for p in every), dtype=np.bool_, count=len(every))
+        return every[keep].reshape(-1, 2)
+
+    @staticmethod
     def _report(what: str, seconds: float, **counts):
         logger.info(f'Finished {what}\n Elapsed time: {seconds}\n'
                     + ''.join(f' {k.replace("_", " ").capitalize()}: {v}\n' for k, v in counts.items()))
@@ -222,9 +248,7 @@ class Matcher(object):
         of `itertools.combinations` (matcher.py:133-165).  Returns `(frames, match_table, images_names)`."""
         t0 = time.time()
         logger.info('Starts matching descriptors.')
-        every = np.array(list(itertools.combinations(images_names.keys(), r=2))).reshape(-1, 2)
-        wanted = every if match_pairs_filter is None else \
-            np.array([p for p in every if match_pairs_filter(p)]).reshape(-1, 2)
+        wanted = self.pair_list(list(images_names.keys()), match_pairs_filter)
         mine = self._shard(wanted)
         run = {'simple': self._simple_matcher, 'super_glue': self._super_glue_matcher}.get(self.matcher_type)
         match_table = run(frames, mine) if run is not None else None

@@ -167,3 +167,30 @@ def test_gloo_world2_gather_tables_and_features():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_pair_list_matches_itertools_and_vectorised_filters():
+    """Matcher.pair_list == filter(f, itertools.combinations(ids, 2)) (matcher.py:143-144) for array-style filters
+    (evaluated once), per-pair filters, constant filters and filters that cannot take arrays."""
+    import itertools
+    import numpy as np
+    from simplesfm_b200.matchers.matcher import Matcher
+    ids = [np.int64(i) for i in range(1, 41)]
+    allowed = {(1, 2), (3, 9), (39, 40)}
+    filters = [None,
+               lambda x: np.abs(x[0] - x[1]) < 5,                     # generate_..._from_scene.py:141
+               lambda x: True,
+               lambda x: False,
+               lambda x: x[0] == 1 and x[1] < 7,                      # raises on arrays -> per pair
+               lambda x: (int(x[0]), int(x[1])) in allowed,           # scalar-only -> per pair
+               lambda x: (x[0] + x[1]) % 3 == 0]
+    for f in filters:
+        every = list(itertools.combinations(ids, 2))
+        ref = np.array([p for p in every if (f is None or f(np.array(p)))]).reshape(-1, 2)
+        got = Matcher.pair_list(ids, f)
+        assert got.shape == ref.shape and np.array_equal(got, ref)
+    assert Matcher.pair_list([np.int64(1)], lambda x: True).shape == (0, 2)
+    # a filter whose array answer disagrees with its per-pair answer must not be trusted
+    tricky = lambda x: (np.asarray(x[0]) > 0) if np.ndim(x[0]) else (x[0] % 2 == 0)
+    ref = np.array([p for p in itertools.combinations(ids, 2) if tricky(np.array(p))]).reshape(-1, 2)
+    assert np.array_equal(Matcher.pair_list(ids, tricky), ref)
