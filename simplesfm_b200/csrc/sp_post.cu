@@ -64,8 +64,53 @@ __device__ __forceinline__ void pool_sep(const float* __restrict__ in, float* __
   __syncthreads();
 }
 
+// radius-4 fast path (the reference default): every thread produces FOUR neighbouring outputs from 16-byte shared
+// loads (3 per 4 outputs in the row pass, 9 in the column pass, instead of 9 scalar loads per output) and
+// three-input maxima.  max is exact and order-independent, so the result equals the scalar chain bit for bit.
+__device__ __forceinline__ float fmax3f(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ void pool_sep_r4(const float* __restrict__ in, float* __restrict__ tmp,
+                                            float* __restrict__ out, int T, int mg) {
+  const int lo = mg, hi = T - mg;
+  const int olo = mg + 4, ohi = T - mg - 4;
+  const int wout = ohi - olo, hin = hi - lo;     // T % 4 == 0 and mg % 4 == 0: wout % 4 == 0, 16-byte aligned x
+  if (wout <= 0) return;
+  const int wq = wout >> 2;
+  for (int i = threadIdx.x; i < hin * wq; i += blockDim.x) {
+    const int y = lo + i / wq, x = olo + 4 * (i % wq);
+    const float4 A = *reinterpret_cast<const float4*>(in + y * T + x - 4);
+    const float4 B = *reinterpret_cast<const float4*>(in + y * T + x);
+    const float4 C = *reinterpret_cast<const float4*>(in + y * T + x + 4);
+    // inputs x-4 .. x+7 = A.xyzw B.xyzw C.xyzw ; output k covers inputs k .. k+8
+    const float core = fmaxf(fmax3f(A.w, B.x, B.y), fmax3f(B.z, B.w, C.x));   // inputs 3 .. 8
+    float4 o;
+    o.x = fmaxf(core, fmax3f(A.x, A.y, A.z));
+    o.y = fmax3f(core, fmaxf(A.y, A.z), C.y);
+    o.z = fmax3f(core, A.z, fmaxf(C.y, C.z));
+    o.w = fmaxf(core, fmax3f(C.y, C.z, C.w));
+    *reinterpret_cast<float4*>(tmp + y * T + x) = o;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < wout * wq; i += blockDim.x) {
+    const int y = olo + i / wq, x = olo + 4 * (i % wq);
+    float4 v[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) v[k] = *reinterpret_cast<const float4*>(tmp + (y - 4 + k) * T + x);
+    float4 o;
+    o.x = fmax3f(fmax3f(v[0].x, v[1].x, v[2].x), fmax3f(v[3].x, v[4].x, v[5].x), fmax3f(v[6].x, v[7].x, v[8].x));
+    o.y = fmax3f(fmax3f(v[0].y, v[1].y, v[2].y), fmax3f(v[3].y, v[4].y, v[5].y), fmax3f(v[6].y, v[7].y, v[8].y));
+    o.z = fmax3f(fmax3f(v[0].z, v[1].z, v[2].z), fmax3f(v[3].z, v[4].z, v[5].z), fmax3f(v[6].z, v[7].z, v[8].z));
+    o.w = fmax3f(fmax3f(v[0].w, v[1].w, v[2].w), fmax3f(v[3].w, v[4].w, v[5].w), fmax3f(v[6].w, v[7].w, v[8].w));
+    *reinterpret_cast<float4*>(out + y * T + x) = o;
+  }
+  __syncthreads();
+}
+
 __global__ void nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H, int W, int r) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int halo = 5 * r;
   const int T = NMS_TILE + 2 * halo;
   float* s = sm;              // scores (-inf outside the image)
@@ -83,7 +128,7 @@ __global__ void nms_kernel(const float* __restrict__ scores, float* __restrict__
     s[i] = in ? src[(long long)y * W + x] : -INFINITY;
   }
   __syncthreads();
-  pool_sep(s, tmp, pl, T, r, 0);           // valid on margin r
+  if (r == 4) pool_sep_r4(s, tmp, pl, T, 0); else pool_sep(s, tmp, pl, T, r, 0);   // valid on margin r
   for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
     int ty = i / T, tx = i % T;
     int y = y0 + ty, x = x0 + tx;
@@ -96,7 +141,7 @@ __global__ void nms_kernel(const float* __restrict__ scores, float* __restrict__
     for (int i = threadIdx.x; i < T * T; i += blockDim.x) a[i] = mx[i] ? 1.f : 0.f;
     __syncthreads();
     const int m1 = r * (1 + 2 * round);
-    pool_sep(a, tmp, pl, T, r, m1);       // pl > 0  <=> suppressed neighbourhood (valid on margin m1 + r)
+    if (r == 4) pool_sep_r4(a, tmp, pl, T, m1); else pool_sep(a, tmp, pl, T, r, m1);   // pl > 0 <=> suppressed neighbourhood (valid on margin m1 + r)
     for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
       int y = y0 + i / T, x = x0 + i % T;
       bool in = y >= 0 && y < H && x >= 0 && x < W;
@@ -108,7 +153,7 @@ __global__ void nms_kernel(const float* __restrict__ scores, float* __restrict__
       mx[i] = (mx[i] & 1) | (supp ? 2 : 0);
     }
     __syncthreads();
-    pool_sep(a, tmp, pl, T, r, m1 + r);   // valid on margin m1 + 2r
+    if (r == 4) pool_sep_r4(a, tmp, pl, T, m1 + r); else pool_sep(a, tmp, pl, T, r, m1 + r);   // valid on margin m1 + 2r
     for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
       int ty = i / T, tx = i % T;
       int y = y0 + ty, x = x0 + tx;
