@@ -148,6 +148,10 @@ SFM_API int sfm_attention(const float* query, const float* key, const float* val
 SFM_API size_t sfm_sinkhorn_workspace_bytes(int B, int N, int M);
 SFM_API int sfm_log_optimal_transport(const float* scores, int B, int N, int M, float alpha, int iters, float* Z,
                               void* workspace, size_t workspace_bytes, void* stream);
+/* log_sinkhorn_iterations (superglue.py:142-148) on ARBITRARY couplings Z (B,m,n) and marginals log_mu (B,m),
+ * log_nu (B,n): out = Z + u + v after `iters` iterations from u = v = 0.  workspace: (B*m + B*n) floats. */
+SFM_API int sfm_log_sinkhorn_iterations(const float* Z, const float* log_mu, const float* log_nu, int B, int m, int n,
+                                        int iters, float* out, void* workspace, size_t workspace_bytes, void* stream);
 /* Sinkhorn + mutual-NN + threshold without materialising Z (superglue.py:268-283; BASELINE config 5) */
 SFM_API int sfm_sinkhorn_match(const float* scores, int B, int N, int M, float alpha, int iters, float match_threshold,
                        int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,

@@ -62,6 +62,8 @@ _SIGNATURES = {
     "sfm_sinkhorn_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "sfm_log_optimal_transport": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p,
                                             C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sfm_log_sinkhorn_iterations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfm_sinkhorn_match": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                      C.c_void_p]),

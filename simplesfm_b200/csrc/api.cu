@@ -152,6 +152,7 @@ int sfm_create(int device, sfm_handle_t* out) {
   sfm_ctx* h = new sfm_ctx();
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
+  h->tmaps = tc::tmap_cache_create();
   *out = h;
   return SFM_OK;
 }
@@ -193,6 +194,7 @@ int sfm_destroy(sfm_handle_t h) {
     }
   for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
+  tc::tmap_cache_destroy(h->tmaps);
   delete h;
   return SFM_OK;
 }
@@ -467,6 +469,19 @@ int sfm_log_optimal_transport(const float* scores, int B, int N, int M, float al
   return sinkhorn_write_Z(s, Z, (cudaStream_t)stream);
 }
 
+int sfm_log_sinkhorn_iterations(const float* Z, const float* log_mu, const float* log_nu, int B, int m, int n, int iters,
+                                float* out, void* ws, size_t ws_bytes, void* stream) {
+  SFM_REQUIRE(B == 0 || (Z && log_mu && log_nu && out && ws), "sfm_log_sinkhorn_iterations: NULL argument");
+  SFM_REQUIRE(B >= 0 && m > 0 && n > 0, "sfm_log_sinkhorn_iterations: bad dims");
+  const size_t need = ((size_t)B * m + (size_t)B * n) * sizeof(float);
+  if (ws_bytes < need) {
+    set_error("sfm_log_sinkhorn_iterations: workspace too small (%zu bytes given, %zu needed)", ws_bytes, need);
+    return SFM_ERR_WORKSPACE;
+  }
+  float* u = (float*)ws;
+  return log_sinkhorn_general(Z, log_mu, log_nu, B, m, n, iters, out, u, u + (size_t)B * m, (cudaStream_t)stream);
+}
+
 int sfm_sinkhorn_match(const float* scores, int B, int N, int M, float alpha, int iters, float match_threshold,
                        int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1, void* ws,
                        size_t ws_bytes, void* stream) {
@@ -596,6 +611,7 @@ int sfm_tc_gemm(sfm_handle_t h, const void* A, const void* A2, const void* W, in
   g.bias = bias; g.alpha = alpha; g.relu = relu;
   g.out_h = (__nv_bfloat16*)out_bf16; g.out_h_ld = N;
   g.out_f = out_f32; g.out_f_ld = N; g.accumulate_f = accumulate;
+  g.tmaps = h->tmaps;
   return tc::tc_gemm(g, h->sm_count, (cudaStream_t)stream);
 }
 
@@ -607,7 +623,8 @@ int sfm_tc_attention(sfm_handle_t h, const void* qkv, long long rows_total, int 
   a.qkv = (const __nv_bfloat16*)qkv; a.rows_total = rows_total; a.out = (__nv_bfloat16*)out_bf16; a.B = B;
   a.Nq[0] = Nq0; a.Nk[0] = Nk0; a.q_row0[0] = q_row0_0; a.k_row0[0] = k_row0_0;
   a.Nq[1] = Nq1; a.Nk[1] = Nk1; a.q_row0[1] = q_row0_1; a.k_row0[1] = k_row0_1;
-  return tc::tc_attention(a, (cudaStream_t)stream);
+  a.tmaps = h->tmaps;
+  return tc::tc_attention(a, h->sm_count, (cudaStream_t)stream);
 }
 
 int sfm_tc_conv3x3(sfm_handle_t h, const void* in_nhwc, const void* w, const float* bias, void* out_nhwc, int n, int H,

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
+#include <atomic>
 
 #define SFM_OK 0
 #define SFM_ERR_INVALID (-1)
@@ -45,6 +46,36 @@ void count_launches(long long n);
   do {                                  \
     int rc__ = (expr);                  \
     if (rc__ != SFM_OK) return rc__;    \
+  } while (0)
+
+// One-time per-DEVICE setup of a kernel (opt-in to > 48 KB of dynamic shared memory is a per-device function
+// attribute).  One instance per kernel instantiation; a bit per device ordinal, set after the setup succeeded,
+// so a second GPU in the same process -- or a second thread racing on the first call -- still gets configured
+// (the setup is idempotent).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done[2];
+  PerDeviceOnce() { done[0] = 0; done[1] = 0; }
+  template <typename F>
+  int run(F&& setup) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__);
+    std::atomic<unsigned long long>& word = done[(dev >> 6) & 1];
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (word.load(std::memory_order_acquire) & bit) return SFM_OK;
+    const int rc = setup();
+    if (rc == SFM_OK) word.fetch_or(bit, std::memory_order_release);
+    return rc;
+  }
+};
+// opt a kernel in to `smem` bytes of dynamic shared memory on the current device (once per device)
+#define SFM_SMEM_OPT_IN(kernel, smem)                                                                         \
+  do {                                                                                                        \
+    static ::sfm::PerDeviceOnce once__;                                                                       \
+    SFM_TRY(once__.run([&]() -> int {                                                                         \
+      SFM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));       \
+      return SFM_OK;                                                                                          \
+    }));                                                                                                      \
   } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -60,8 +60,11 @@ struct SpWeights {
 
 enum { SFM_PROF_LINEAR = 0, SFM_PROF_ATTENTION = 1, SFM_PROF_SINKHORN = 2, SFM_PROF_OTHER = 3, SFM_PROF_KINDS = 4 };
 
+namespace sfm { namespace tc { struct TmapCache; } }
+
 struct sfm_ctx {
   int device = 0;
+  sfm::tc::TmapCache* tmaps = nullptr;   // encoded TMA tensor maps of this handle's launches
   int sm_count = 148;
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[SFM_PROF_KINDS];  // recorded this window

@@ -60,6 +60,10 @@ int simple_mutual(const float* max0, const int* idx0, const int* idx1, int N, fl
 // optional: write the full (B, N+1, M+1) log-assignment (what log_optimal_transport returns)
 int sinkhorn_write_Z(const SinkhornArgs& a, float* Z, cudaStream_t st);
 
+// log_sinkhorn_iterations on arbitrary couplings / marginals (superglue.py:142-148); u [B,m], v [B,n] scratch
+int log_sinkhorn_general(const float* Z, const float* log_mu, const float* log_nu, int B, int m, int n, int iters,
+                         float* out, float* u, float* v, cudaStream_t st);
+
 // (L,2) uint32 match-table compaction per pair: rows [i, matches0[i]] for matches0[i] > -1
 int compact_matches(const long long* matches0, int B, int N, unsigned* tables, int* lengths, cudaStream_t st);
 

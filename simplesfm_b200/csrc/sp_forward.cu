@@ -79,6 +79,7 @@ int head1x1(sfm_ctx* h, const SpConv& cv, const __nv_bfloat16* in, float* out, l
   g.A = in; g.lda = cv.cin; g.a_rows = rows; g.W = cv.w_h; g.ldw = cv.cin; g.w_rows = cv.cout;
   g.M = (int)rows; g.N = cv.cout; g.K = cv.cin; g.K1 = cv.cin; g.bias = cv.b;
   g.out_f = out; g.out_f_ld = cv.cout;
+  g.tmaps = h->tmaps;
   return tc::tc_gemm(g, h->sm_count, st);
 }
 

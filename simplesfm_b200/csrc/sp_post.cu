@@ -426,15 +426,15 @@ int sp_softmax_shuffle(const float* logits, int ldl, float* out, int n_img, int 
 
 int sp_nms(const float* scores, float* out, int n_img, int H, int W, int radius, cudaStream_t st) {
   SFM_REQUIRE(radius >= 0, "simple_nms: nms_radius must be >= 0");
-  SFM_REQUIRE(radius <= 9, "simple_nms: nms_radius > 9 is not supported by the tiled kernel (got %d)", radius);
+  SFM_REQUIRE(radius <= 8, "simple_nms: nms_radius > 8 is not supported by the tiled kernel (got %d)", radius);
   if (n_img == 0 || H == 0 || W == 0) return SFM_OK;
   int T = NMS_TILE + 10 * radius;
   size_t smem = (size_t)T * T * (4 * sizeof(float) + 1) + 16;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    SFM_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  // one opt-in per device to the largest dynamic shared memory a CTA may have on sm_100 (227 KB)
+  constexpr size_t SMEM_MAX = 227 * 1024;
+  SFM_REQUIRE(smem <= SMEM_MAX, "simple_nms: nms_radius %d needs %zu bytes of shared memory per tile (limit %zu)", radius,
+              smem, SMEM_MAX);
+  SFM_SMEM_OPT_IN(nms_kernel, SMEM_MAX);
   dim3 grid(cdiv(W, NMS_TILE), cdiv(H, NMS_TILE), n_img);
   nms_kernel<<<grid, 512, smem, st>>>(scores, out, H, W, radius);
   SFM_LAUNCH_CHECK();

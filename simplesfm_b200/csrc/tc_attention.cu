@@ -6,9 +6,10 @@
 // persistent (one per SM, units strided by the grid): the Q tiles of the next unit are loaded into a second
 // buffer and its first S = Q K^T is issued while the softmax groups still normalise / store the previous
 // unit's output, so barrier setup, TMEM allocation and the load / store latencies are paid once per CTA.
-//   warp 0    : TMA producer (Q tiles per unit, K/V tiles through a 3-stage ring that runs across units)
-//   warp 1    : tcgen05.mma issuer:  S_t = Q_t K_j^T  (SS, fp32 in TMEM),  O_t = P_t V_j  (A = P from TMEM)
-//   warps 2-5 : softmax warpgroup of tile 0 (thread = query row), warps 6-9: tile 1
+//   warp 0     : TMA producer (Q tiles per unit, K/V tiles through a 3-stage ring that runs across units)
+//   warps 1-2  : tcgen05.mma issuers, one per query tile:  S_t = Q_t K_j^T  (SS, fp32 in TMEM),
+//                O_t = P_t V_j  (A = P from TMEM)
+//   warps 3-6  : softmax warpgroup of tile 0 (thread = query row), warps 7-10: tile 1
 // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512)
 // O accumulates in TMEM across K/V tiles.  The softmax threads keep a (possibly stale) reference
 // maximum per row and only rescale O / the running sum when the true maximum has grown by more
@@ -25,7 +26,8 @@ namespace {
 
 constexpr int KV_STAGES = 3;
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, 128-byte swizzled rows
-template <int NT> struct AttCfg { static constexpr int THREADS = 64 + NT * 128; };
+// warp 0: TMA producer; warps 1..NT: one MMA issuer per query tile; then NT softmax warpgroups
+template <int NT> struct AttCfg { static constexpr int SW0 = 1 + NT; static constexpr int THREADS = (1 + NT) * 32 + NT * 128; };
 
 struct AttBars {
   uint64_t q_full[2], q_empty[2];
@@ -58,8 +60,12 @@ __device__ __forceinline__ Unit decode_unit(const TcAttn& p, int u, int units0, 
   return w;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(64 + NT * 128, NT == 1 ? 2 : 1)
+// DBG != 0 only exists in -DSFM_ATT_EXPERIMENTS builds (tools/att_experiments.sh): it removes one stage of the
+// softmax loop at a time to measure what that stage costs (results are then meaningless):
+//   1 no MUFU (FFMA instead of ex2)   2 S is loaded from TMEM only on a unit's first step   4 no P store
+//   8 no row-sum adds   16 no row maximum
+template <int NT, int DBG = 0>
+__global__ void __launch_bounds__(AttCfg<NT>::THREADS, 1)
 tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units0, int qt0, int qt1, int n_units) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -74,11 +80,11 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
     tma_prefetch_desc(&map);
     for (int q = 0; q < 2; q++) {
       mbar_init(&bars->q_full[q], 1);
-      mbar_init(&bars->q_empty[q], 1);
+      mbar_init(&bars->q_empty[q], NT);
     }
     for (int s = 0; s < KV_STAGES; s++) {
       mbar_init(&bars->kv_full[s], 1);
-      mbar_init(&bars->kv_empty[s], 1);
+      mbar_init(&bars->kv_empty[s], NT);
     }
     for (int t = 0; t < NT; t++) {
       mbar_init(&bars->s_full[t], 1);
@@ -117,16 +123,22 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp <= NT) {
+    // ------------------------------------------------------------------ MMA issuers: ONE PER QUERY TILE
+    // Each tile's chain  S_t(g+1) <- s_free_t(g),  P V_t(g) <- p_full_t(g)  is driven by its own thread, so a tile
+    // never waits behind a barrier of the other tile (a single in-order issuer couples the two softmax groups:
+    // its four waits per step form one cycle, and whichever group runs late stalls the other's P V).  The two
+    // tiles share only the K/V ring and the Q buffers, released when BOTH issuers' MMAs on them have completed
+    // (kv_empty / q_empty count NT; tcgen05.commit tracks the issuing thread's own MMAs).
+    const int t = warp - 1;
     if (lane == 0 && blockIdx.x < n_units) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);  // S = Q K^T : B = K tile, K-major
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);   // O = P V   : B = V tile, MN-major
       const uint64_t q_desc0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
       const uint64_t k_desc0 = umma_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t v_desc0 = umma_desc_sw128(smem_u32(sV), 1024, 1024);
-      // S_t of K/V step `stage`, Q buffer qb
-      auto issue_s = [&](int t, int qb, int stage) {
+      // S_t of the K/V tile in ring slot `stage`, Q buffer qb
+      auto issue_s = [&](int qb, int stage) {
         const uint64_t ad = umma_desc_advance(q_desc0, (qb * NT + t) * TILE_BYTES);
         const uint64_t bd = umma_desc_advance(k_desc0, stage * TILE_BYTES);
 #pragma unroll
@@ -135,10 +147,6 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
                   k != 0);
         umma_commit(&bars->s_full[t]);
       };
-      // Issue order follows a STAGGERED schedule: tile 1 runs half a K/V step behind tile 0 (its softmax group
-      // starts late, see below), so that one group's exponentials overlap the other group's TMEM load / maximum /
-      // waits.  Per global step g:  S0(g+1) | PV1(g-1) | S1(g+1) | PV0(g)  -- each behind the barrier that fires
-      // next in that schedule, so the issuer never couples the two groups back into lock-step.
       struct Cursor { int u, it, j, n_kv; bool valid; };
       auto advance = [&](Cursor& c) {
         if (++c.j == c.n_kv) {
@@ -149,61 +157,43 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
           if (c.valid) c.n_kv = decode_unit<NT>(p, c.u, units0, qt0, qt1).n_kv;
         }
       };
-      auto issue_pv = [&](int t, int g, bool first) {
+      Cursor cur{(int)blockIdx.x, 0, 0, decode_unit<NT>(p, blockIdx.x, units0, qt0, qt1).n_kv, true};
+      // very first S of this tile
+      mbar_wait(&bars->q_full[0], 0);
+      mbar_wait(&bars->kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      for (int g = 0; cur.valid; g++) {
+        Cursor nxt = cur;
+        advance(nxt);
+        const bool cur_first = cur.j == 0, cur_last = cur.j + 1 == cur.n_kv;
+        if (nxt.valid) {
+          // S of step g+1 (next K/V tile of this unit, or tile 0 of the next unit with its own Q buffer): issued as
+          // soon as the softmax group holds S_t(g) in registers, so it overlaps the exponentials of step g
+          const int s1 = (g + 1) % KV_STAGES;
+          if (nxt.j == 0) mbar_wait(&bars->q_full[nxt.it & 1], (nxt.it >> 1) & 1);
+          mbar_wait(&bars->kv_full[s1], ((g + 1) / KV_STAGES) & 1);
+          mbar_wait(&bars->s_free[t], g & 1);
+          tc_fence_after();
+          issue_s(nxt.it & 1, s1);
+        }
+        // every S MMA of this tile that reads this unit's Q buffer has been issued
+        if (cur_last) umma_commit(&bars->q_empty[cur.it & 1]);
         mbar_wait(&bars->p_full[t], g & 1);
         tc_fence_after();
         const uint64_t vd = umma_desc_advance(v_desc0, (g % KV_STAGES) * TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < 8; k++)  // 16 keys per step: 16 V rows = 2048 bytes, P advances 8 columns
           umma_ts(tmem + COL_O + t * 64, tmem + COL_P + t * 64 + k * 8, umma_desc_advance(vd, k * 2048), idesc_o,
-                  (first ? 0 : 1) | k);
+                  (cur_first ? 0 : 1) | k);
         umma_commit(&bars->o_full[t]);
-      };
-      Cursor cur{(int)blockIdx.x, 0, 0, decode_unit<NT>(p, blockIdx.x, units0, qt0, qt1).n_kv, true};
-      // very first S of this CTA
-      mbar_wait(&bars->q_full[0], 0);
-      mbar_wait(&bars->kv_full[0], 0);
-      tc_fence_after();
-      for (int t = 0; t < NT; t++) issue_s(t, 0, 0);
-      bool prev_first = false;   // step g-1 was the first of its unit (its P V overwrites O)
-      int g = 0;
-      for (; cur.valid; g++) {
-        Cursor nxt = cur;
-        advance(nxt);
-        const bool cur_first = cur.j == 0, cur_last = cur.j + 1 == cur.n_kv;
-        const int s1 = (g + 1) % KV_STAGES;
-        // S of step g+1 (next K/V tile of this unit, or tile 0 of the next unit with its own Q buffer)
-        auto issue_next_s = [&](int t) {
-          if (!nxt.valid) return;
-          if (t == 0) {
-            if (nxt.j == 0) mbar_wait(&bars->q_full[nxt.it & 1], (nxt.it >> 1) & 1);
-            mbar_wait(&bars->kv_full[s1], ((g + 1) / KV_STAGES) & 1);
-          }
-          mbar_wait(&bars->s_free[t], g & 1);
-          tc_fence_after();
-          issue_s(t, nxt.it & 1, s1);
-        };
-        issue_next_s(0);
-        if (NT > 1 && g > 0) {
-          issue_pv(NT - 1, g - 1, prev_first);
-          umma_commit(&bars->kv_empty[(g - 1) % KV_STAGES]);   // both tiles are done with K/V stage g-1
-        }
-        for (int t = 1; t < NT; t++) issue_next_s(t);
-        // all S MMAs that read this unit's Q buffer have been issued (the next step belongs to another unit)
-        if (cur_last) umma_commit(&bars->q_empty[cur.it & 1]);
-        issue_pv(0, g, cur_first);
-        if (NT == 1) umma_commit(&bars->kv_empty[g % KV_STAGES]);
-        prev_first = cur_first;
+        umma_commit(&bars->kv_empty[g % KV_STAGES]);   // this tile is done with K/V slot g (S_t(g) and P V_t(g))
         cur = nxt;
-      }
-      if (NT > 1 && g > 0) {
-        issue_pv(NT - 1, g - 1, prev_first);
-        umma_commit(&bars->kv_empty[(g - 1) % KV_STAGES]);
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
-    const int t = (warp - 2) >> 2;  // query tile of this warpgroup
+    const int t = (warp - AttCfg<NT>::SW0) >> 2;  // query tile of this warpgroup
     const int quad = warp & 3;      // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
@@ -222,10 +212,12 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
       tc_fence_after();
       const int valid = min(128, Nk - j * 128);  // columns of this tile that are real keys
       uint32_t sv[128];
+      if (!(DBG & 2) || j == 0) {
 #pragma unroll
-      for (int ch = 0; ch < 4; ch++)
-        tmem_ld_32x32(lane_addr + COL_S + t * 128 + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[ch * 32]));
-      tmem_wait_ld();
+        for (int ch = 0; ch < 4; ch++)
+          tmem_ld_32x32(lane_addr + COL_S + t * 128 + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[ch * 32]));
+        tmem_wait_ld();
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_free[t]);   // S_t is in registers: the tensor pipe may overwrite it
@@ -239,10 +231,12 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
       float mxa[8];
 #pragma unroll
       for (int q = 0; q < 8; q++) mxa[q] = fmaxf(__uint_as_float(sv[q]), __uint_as_float(sv[8 + q]));
+      if (!(DBG & 16)) {
 #pragma unroll
-      for (int i = 16; i < 128; i += 16)
+        for (int i = 16; i < 128; i += 16)
 #pragma unroll
-        for (int q = 0; q < 8; q++) mxa[q] = fmax3(mxa[q], __uint_as_float(sv[i + q]), __uint_as_float(sv[i + 8 + q]));
+          for (int q = 0; q < 8; q++) mxa[q] = fmax3(mxa[q], __uint_as_float(sv[i + q]), __uint_as_float(sv[i + 8 + q]));
+      }
       const float mx = fmaxf(fmax3(mxa[0], mxa[1], mxa[2]), fmax3(fmax3(mxa[3], mxa[4], mxa[5]), mxa[6], mxa[7]));
       // lazy rescale decision (the O rescale itself is deferred until S has been consumed, so that
       // the 128 S registers and the O staging registers are never live together)
@@ -260,10 +254,6 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
       }
       const bool any_grow = __any_sync(0xffffffffu, grow);
       const float mc = m_used * c;
-      if (j > 0) {  // P V (j-1) must have consumed P_t before it is overwritten (and O_t must be quiescent)
-        mbar_wait(&bars->o_full[t], (g - 1) & 1);
-        tc_fence_after();
-      }
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int half = 0; half < 2; half++) {   // two 64-key halves keep the packed-P registers short-lived
@@ -271,15 +261,25 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
 #pragma unroll
         for (int i = 0; i < 64; i += 4) {
           const int e = half * 64 + i;
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), c, -mc));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), c, -mc));
-          const float p2 = fast_exp2(fmaf(__uint_as_float(sv[e + 2]), c, -mc));
-          const float p3 = fast_exp2(fmaf(__uint_as_float(sv[e + 3]), c, -mc));
-          ls[0] += p0; ls[1] += p1; ls[2] += p2; ls[3] += p3;
+          auto ex = [](float x) { return (DBG & 1) ? fmaf(x, 0.5f, 1.0f) : fast_exp2(x); };
+          const float p0 = ex(fmaf(__uint_as_float(sv[e]), c, -mc));
+          const float p1 = ex(fmaf(__uint_as_float(sv[e + 1]), c, -mc));
+          const float p2 = ex(fmaf(__uint_as_float(sv[e + 2]), c, -mc));
+          const float p3 = ex(fmaf(__uint_as_float(sv[e + 3]), c, -mc));
+          if (!(DBG & 8)) { ls[0] += p0; ls[1] += p1; ls[2] += p2; ls[3] += p3; }
           pk[i >> 1] = pack_bf16(p0, p1);
           pk[(i >> 1) + 1] = pack_bf16(p2, p3);
         }
-        tmem_st_32x32(lane_addr + COL_P + t * 64 + half * 32, pk);
+        if (half == 0 && j > 0) {
+          // P V (j-1) must have consumed P_t before it is overwritten (and O_t must be quiescent).  The wait sits
+          // AFTER the first 64 exponentials: they only need registers, so the previous step's P V (issue + 256
+          // tensor clocks + commit) completes behind ~512 MUFU clocks instead of stalling the group (the wait in
+          // front of the loop took 13.5 % of this kernel's stall samples, profiles/r2_attention_ncu.txt)
+          mbar_wait(&bars->o_full[t], (g - 1) & 1);
+          tc_fence_after();
+        }
+        if (!(DBG & 4)) tmem_st_32x32(lane_addr + COL_P + t * 64 + half * 32, pk);
+        else if (pk[(j + half) & 31] == 0x12345678u) l_run += 1.f;   // keep the values live
       }
       l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       if (any_grow) {   // warp-uniform: rescale the running output of rows whose reference maximum moved
@@ -325,40 +325,43 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
   if (warp == 1) tmem_dealloc<NT * 256>(tmem);
 }
 
-template <int NT>
+template <int NT, int DBG = 0>
 int launch_att(const TcAttn& p, const CUtensorMap& map, int num_sms, cudaStream_t st) {
   const int qt0 = cdiv(p.Nq[0], NT * 128), qt1 = p.Nq[1] > 0 ? cdiv(p.Nq[1], NT * 128) : 0;
   const int units0 = p.B * 4 * qt0, units1 = p.B * 4 * qt1;
   const int n_units = units0 + units1;
   const size_t smem = (size_t)(2 * NT + 2 * KV_STAGES) * TILE_BYTES + sizeof(AttBars) + 1024;
-  static bool configured = false;
-  if (!configured) {
-    SFM_CUDA(cudaFuncSetAttribute(tc_attention_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
-  const int ctas_per_sm = NT == 1 ? 2 : 1;
-  const int grid = std::min(n_units, num_sms * ctas_per_sm);
-  tc_attention_kernel<NT><<<grid, AttCfg<NT>::THREADS, smem, st>>>(map, p, units0, qt0, qt1 > 0 ? qt1 : 1, n_units);
+  SFM_SMEM_OPT_IN((tc_attention_kernel<NT, DBG>), smem);
+  const int grid = std::min(n_units, num_sms);
+  tc_attention_kernel<NT, DBG><<<grid, AttCfg<NT>::THREADS, smem, st>>>(map, p, units0, qt0, qt1 > 0 ? qt1 : 1, n_units);
   SFM_LAUNCH_CHECK();
   return SFM_OK;
 }
 
 }  // namespace
 
-int tc_attention(const TcAttn& p, cudaStream_t st) {
+int tc_attention(const TcAttn& p, int num_sms, cudaStream_t st) {
   SFM_REQUIRE(p.B > 0 && p.Nq[0] > 0 && p.Nk[0] > 0 && p.Nq[1] >= 0, "tc_attention: bad dims");
   CUtensorMap map;
-  SFM_TRY(make_tmap_bf16(&map, p.qkv, p.rows_total, 768, 768, 128));
-  static int nt = getenv("SFM_ATT_NT") ? atoi(getenv("SFM_ATT_NT")) : 2;
-  static int stagger = getenv("SFM_ATT_STAGGER") ? atoi(getenv("SFM_ATT_STAGGER")) : 1;
+  SFM_TRY(get_tmap_bf16(p.tmaps, &map, p.qkv, p.rows_total, 768, 768, 128));
+  // tuning knobs are read from the environment once per process (read-only afterwards)
+  static const int nt = getenv("SFM_ATT_NT") ? atoi(getenv("SFM_ATT_NT")) : 2;
+  static const int stagger = getenv("SFM_ATT_STAGGER") ? atoi(getenv("SFM_ATT_STAGGER")) : 1;
   TcAttn q = p;
   q.stagger = stagger;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    SFM_CUDA(cudaGetDevice(&dev));
-    SFM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  SFM_REQUIRE(num_sms > 0, "tc_attention: bad SM count");
+#ifdef SFM_ATT_EXPERIMENTS
+  switch (getenv("SFM_ATT_DBG") ? atoi(getenv("SFM_ATT_DBG")) : 0) {
+    case 1: return launch_att<2, 1>(q, map, num_sms, st);
+    case 2: return launch_att<2, 2>(q, map, num_sms, st);
+    case 4: return launch_att<2, 4>(q, map, num_sms, st);
+    case 8: return launch_att<2, 8>(q, map, num_sms, st);
+    case 16: return launch_att<2, 16>(q, map, num_sms, st);
+    case 9: return launch_att<2, 9>(q, map, num_sms, st);
+    case 31: return launch_att<2, 31>(q, map, num_sms, st);
+    default: break;
   }
+#endif
   if (nt == 1) return launch_att<1>(q, map, num_sms, st);
   return launch_att<2>(q, map, num_sms, st);
 }

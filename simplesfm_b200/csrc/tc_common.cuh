@@ -251,5 +251,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                    uint32_t box_rows);
 
+// Per-handle cache of encoded tensor maps.  A map depends only on (base, rows, cols, ld, box rows) -- never on the
+// data -- so an entry can be reused for as long as the key matches; the launch sequence of a forward pass asks for
+// the same few dozen maps over and over (workspaces are grow-only), which makes the driver encode a once-per-shape
+// cost instead of a per-launch one.  Direct-mapped, guarded by a mutex (handles may be shared between host threads).
+struct TmapCache;
+TmapCache* tmap_cache_create();
+void tmap_cache_destroy(TmapCache* c);
+// `cache` may be null (no caching)
+int get_tmap_bf16(TmapCache* cache, CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                  uint64_t ld_elems, uint32_t box_rows);
+
 }  // namespace tc
 }  // namespace sfm

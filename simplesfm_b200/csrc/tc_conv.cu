@@ -237,11 +237,7 @@ int launch_conv(const TcConv& p, int num_sms, cudaStream_t st) {
   const int tiles = p.n * cdiv(p.H, 8) * cdiv(p.W, 16);
   const size_t smem = (size_t)CONV_STAGES * (A_BYTES + COUT * 128) + 2 * SLAB + COUT * sizeof(float) + sizeof(ConvBars) +
                       1024;
-  static bool configured = false;
-  if (!configured) {
-    SFM_CUDA(cudaFuncSetAttribute(tc_conv3x3_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  SFM_SMEM_OPT_IN(tc_conv3x3_kernel<COUT>, smem);
   const int grid = tiles < num_sms ? tiles : num_sms;
   tc_conv3x3_kernel<COUT><<<grid, CONV_THREADS, smem, st>>>(mIn, mW, mOut, p);
   SFM_LAUNCH_CHECK();

@@ -12,6 +12,8 @@
 #include "tc_common.cuh"
 #include "tc_path.cuh"
 #include <stdlib.h>
+#include <mutex>
+#include <new>
 
 namespace sfm {
 namespace tc {
@@ -98,12 +100,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr int HALF = BN / 2;  // columns per epilogue warpgroup
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per-role wait-cycle counters exist only in debug builds (SFM_EXTRA_NVCC_FLAGS=-DSFM_TC_DEBUG_BUILD)
+#ifdef SFM_TC_DEBUG_BUILD
   long long dbg_wait[4] = {0, 0, 0, 0};
   const long long dbg_t0 = clock64();
-#ifdef SFM_TC_DEBUG_BUILD
 #define DBG_WAIT(slot, stmt) { long long t_ = clock64(); stmt; dbg_wait[slot] += clock64() - t_; }
+  const int DBG_FLAGS = p.dbg_flags;   // bit mask that switches epilogue stages off (bisecting stalls)
 #else
 #define DBG_WAIT(slot, stmt) { stmt; }
+  constexpr int DBG_FLAGS = 0;
 #endif
 
   if (warp == 0 && lane == 0) {
@@ -425,11 +430,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t tcol0 = lane_addr + buf * BN + wg * HALF;
         constexpr int NCH = HALF / 32;
         uint32_t r[2][32];
-        if (!(p.dbg_flags & 2)) tmem_ld_32x32(tcol0, r[0]);
+        if (!(DBG_FLAGS & 2)) tmem_ld_32x32(tcol0, r[0]);
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
           DBG_WAIT(3, tmem_wait_ld());
-          if (c + 1 < NCH && !(p.dbg_flags & 2)) tmem_ld_32x32(tcol0 + (c + 1) * 32, r[(c + 1) & 1]);
+          if (c + 1 < NCH && !(DBG_FLAGS & 2)) tmem_ld_32x32(tcol0 + (c + 1) * 32, r[(c + 1) & 1]);
           const int cl = wg * HALF + c * 32;  // first column of this chunk inside the panel
           const int n0 = panel * BN + cl;
           float v[32];
@@ -467,11 +472,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               }
             }
           }
-          if (p.out_h != nullptr && !(p.dbg_flags & 1)) {
+          if (p.out_h != nullptr && !(DBG_FLAGS & 1)) {
             // bf16 slab: 128 rows x 64 columns, 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
             if ((c & 1) == 0) {
               DBG_WAIT(1, if (wg_tid == 0) tma_store_wait_read());  // previous store has finished reading the slab
-              if (!(p.dbg_flags & 8)) { DBG_WAIT(2, named_bar_sync(2 + wg, 128)); }
+              if (!(DBG_FLAGS & 8)) { DBG_WAIT(2, named_bar_sync(2 + wg, 128)); }
             }
             const uint32_t rowa = slab_u32 + row_in_tile * 128;
 #pragma unroll
@@ -482,11 +487,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                      pack_bf16(v[8 * j + 6], v[8 * j + 7]));
             }
             if ((c & 1) == 1 || NCH == 1) {
-              if (!(p.dbg_flags & 16)) { DBG_WAIT(1, fence_proxy_async()); }
-              if (!(p.dbg_flags & 8)) { DBG_WAIT(2, named_bar_sync(2 + wg, 128)); }
+              if (!(DBG_FLAGS & 16)) { DBG_WAIT(1, fence_proxy_async()); }
+              if (!(DBG_FLAGS & 8)) { DBG_WAIT(2, named_bar_sync(2 + wg, 128)); }
               if (wg_tid == 0) {
                 const int col = panel * BN + wg * HALF + (c >> 1) * 64;
-                if (col < p.N && !(p.dbg_flags & 4)) tma_store_2d(&mapO, slab, col, p.out_row_base + b * p.out_row_stride + mt * BM);
+                if (col < p.N && !(DBG_FLAGS & 4)) tma_store_2d(&mapO, slab, col, p.out_row_base + b * p.out_row_stride + mt * BM);
                 tma_store_commit();
               }
               if (p.stat_partial != nullptr) {
@@ -523,16 +528,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     if (!RMW && p.out_h != nullptr && wg_tid == 0) tma_store_wait_all();
   }
+#ifdef SFM_TC_DEBUG_BUILD
   if (p.dbg != nullptr && lane == 0 && (warp <= 2)) {
     long long* d = p.dbg + ((long long)blockIdx.x * 3 + warp) * 6;
     d[0] = dbg_wait[0]; d[1] = dbg_wait[1]; d[2] = dbg_wait[2]; d[3] = dbg_wait[3]; d[4] = clock64() - dbg_t0;
   }
+#endif
   tc_fence_before();
   __syncthreads();
   if (CG2) cluster_sync_all();   // no remote arrive / pair-wide MMA may still target a CTA that has left
   if (warp == 1) {
     if (CG2) tmem_dealloc_pair<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
+}
+
+// tuning knobs: read from the environment once per process, read-only afterwards
+struct GemmEnv {
+  int l2_prefetch, cg2, cg2x;
+};
+const GemmEnv& gemm_env() {
+  static const GemmEnv e = {getenv("SFM_TC_PREFETCH") ? atoi(getenv("SFM_TC_PREFETCH")) : 2,   // bit 0: A tiles, bit 1: residual
+                            getenv("SFM_TC_CG2") ? atoi(getenv("SFM_TC_CG2")) : 1,
+                            getenv("SFM_TC_CG2X") ? atoi(getenv("SFM_TC_CG2X")) : 0};           // measured neutral: opt-in
+  return e;
 }
 
 template <int BN, int KBLOCKS, bool XF = false, bool RMW = false, bool CG2 = false>
@@ -551,19 +569,16 @@ int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, co
   p.cpp = cpp;
   const size_t smem = (size_t)KBLOCKS * (CG2 ? BN / 2 : BN) * 128 + STAGES * A_STAGE_BYTES + 2 * SLAB_BYTES +
                       BN * sizeof(float) + sizeof(Barriers) + 1024;
-  static bool configured = false;
-  if (!configured) {
-    SFM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, KBLOCKS, XF, RMW, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    configured = true;
-  }
-  static long long* dbg = nullptr;
+  SFM_SMEM_OPT_IN((tc_gemm_kernel<BN, KBLOCKS, XF, RMW, CG2>), smem);
+  p.l2_prefetch = gemm_env().l2_prefetch;
+#ifdef SFM_TC_DEBUG_BUILD
+  static long long* dbg = nullptr;   // debug builds only: single device, single thread
   const bool want_dbg = getenv("SFM_TC_DEBUG") != nullptr;
   if (want_dbg && dbg == nullptr) cudaMalloc(&dbg, 148 * 3 * 6 * sizeof(long long));
   p.dbg = want_dbg ? dbg : nullptr;
   p.dbg_flags = getenv("SFM_TC_FLAGS") ? atoi(getenv("SFM_TC_FLAGS")) : 0;
-  p.l2_prefetch = getenv("SFM_TC_PREFETCH") ? atoi(getenv("SFM_TC_PREFETCH")) : 2;   // bit 0: A tiles, bit 1: residual
   if (want_dbg) cudaMemsetAsync(dbg, 0, 148 * 3 * 6 * sizeof(long long), st);
+#endif
   if (CG2) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * n_slots * cpp);
@@ -582,6 +597,7 @@ int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, co
     tc_gemm_kernel<BN, KBLOCKS, XF, RMW, CG2><<<n_slots * cpp, XF ? GEMM_THREADS + 128 : GEMM_THREADS, smem, st>>>(mA, mA2, mW, mO, p);
   }
   SFM_LAUNCH_CHECK();
+#ifdef SFM_TC_DEBUG_BUILD
   if (want_dbg) {
     static long long host[148 * 3 * 6];
     cudaStreamSynchronize(st);
@@ -596,6 +612,7 @@ int launch(const TcGemm& p_in, const CUtensorMap& mA, const CUtensorMap& mA2, co
       }
     }
   }
+#endif
   return SFM_OK;
 }
 
@@ -639,6 +656,39 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
   return SFM_OK;
 }
 
+struct TmapCache {
+  static constexpr int SLOTS = 256;
+  struct Entry {
+    const void* base = nullptr;
+    uint64_t rows = 0, cols = 0, ld = 0;
+    uint32_t box = 0;
+    bool valid = false;
+    CUtensorMap map;
+  };
+  std::mutex mu;
+  Entry e[SLOTS];
+};
+TmapCache* tmap_cache_create() { return new (std::nothrow) TmapCache(); }
+void tmap_cache_destroy(TmapCache* c) { delete c; }
+
+int get_tmap_bf16(TmapCache* cache, CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                  uint64_t ld_elems, uint32_t box_rows) {
+  if (cache == nullptr) return make_tmap_bf16(out, base, rows, cols, ld_elems, box_rows);
+  uint64_t hsh = (reinterpret_cast<uintptr_t>(base) >> 8) * 0x9E3779B97F4A7C15ull;
+  hsh ^= (rows * 0xC2B2AE3D27D4EB4Full) ^ (cols << 20) ^ (ld_elems << 9) ^ box_rows;
+  hsh ^= hsh >> 29;
+  std::lock_guard<std::mutex> lock(cache->mu);
+  TmapCache::Entry& en = cache->e[hsh % TmapCache::SLOTS];
+  if (!(en.valid && en.base == base && en.rows == rows && en.cols == cols && en.ld == ld_elems && en.box == box_rows)) {
+    en.valid = false;
+    SFM_TRY(make_tmap_bf16(&en.map, base, rows, cols, ld_elems, box_rows));
+    en.base = base; en.rows = rows; en.cols = cols; en.ld = ld_elems; en.box = box_rows;
+    en.valid = true;
+  }
+  *out = en.map;
+  return SFM_OK;
+}
+
 int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
   SFM_REQUIRE(p.K == 128 || p.K == 256 || p.K == 512, "tc_gemm: K must be 128, 256 or 512 (got %d)", p.K);
   SFM_REQUIRE(p.M > 0 && p.N > 0 && p.batch > 0, "tc_gemm: bad dims");
@@ -651,24 +701,24 @@ int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st) {
                                         p.xf_rows1 % 128 == 0 && p.xf_T0 % 128 == 0 && p.xf_G >= 1),
               "tc_gemm: fused BatchNorm apply needs K = 512 and statistic groups that are whole 128-row tiles");
   CUtensorMap mA, mA2, mW, mO;
-  SFM_TRY(make_tmap_bf16(&mA, p.A, p.a_rows, p.K1, p.lda, BM));
+  SFM_TRY(get_tmap_bf16(p.tmaps, &mA, p.A, p.a_rows, p.K1, p.lda, BM));
   if (p.K1 < p.K)
-    SFM_TRY(make_tmap_bf16(&mA2, p.A2, p.a_rows, p.K - p.K1, p.lda2, BM));
+    SFM_TRY(get_tmap_bf16(p.tmaps, &mA2, p.A2, p.a_rows, p.K - p.K1, p.lda2, BM));
   else
     mA2 = mA;
   const bool wide = (p.K <= 256) && (p.N > 128);
   // CTA-pair kernel: plain bf16-output GEMMs whose rows / columns are whole 256-wide pair tiles
-  static const int cg2_env = getenv("SFM_TC_CG2") ? atoi(getenv("SFM_TC_CG2")) : 1;
+  const int cg2_env = gemm_env().cg2;
   const bool accum_any = p.accumulate_f != 0 || p.out_f != nullptr;
   const bool cg2 = cg2_env && !accum_any && p.xf_scale == nullptr && p.out_h != nullptr && p.batch == 1 &&
                    p.M % 256 == 0 && p.N % 256 == 0 && (p.K == 256 || p.K == 512) && num_sms % 2 == 0;
-  static const int cg2x_on = getenv("SFM_TC_CG2X") ? atoi(getenv("SFM_TC_CG2X")) : 0;   // measured neutral: opt-in
+  const int cg2x_on = gemm_env().cg2x;
   const bool cg2x = cg2x_on && p.xf_scale != nullptr && p.accumulate_f && p.batch == 1 && p.M % 256 == 0 &&
                     p.N % 128 == 0 && p.K == 512 && num_sms % 2 == 0;
-  SFM_TRY(make_tmap_bf16(&mW, p.W, p.w_rows, p.K, p.ldw, cg2x ? 64 : ((wide && !cg2) ? 256 : 128)));
+  SFM_TRY(get_tmap_bf16(p.tmaps, &mW, p.W, p.w_rows, p.K, p.ldw, cg2x ? 64 : ((wide && !cg2) ? 256 : 128)));
   // output map: rows beyond M and columns beyond N are clipped by the TMA unit
   if (p.out_h != nullptr)
-    SFM_TRY(make_tmap_bf16(&mO, p.out_h, p.M, p.N, p.out_h_ld, 128));
+    SFM_TRY(get_tmap_bf16(p.tmaps, &mO, p.out_h, p.M, p.N, p.out_h_ld, 128));
   else
     mO = mA;
   TcGemm q = p;

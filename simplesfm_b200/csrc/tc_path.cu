@@ -30,6 +30,7 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
                     float* out_f, int accumulate) {
     ProfScope ps(h, SFM_PROF_LINEAR, st);
     TcGemm g;
+    g.tmaps = h->tmaps;
     g.A = A; g.lda = lda; g.A2 = A2; g.lda2 = lda2; g.a_rows = T;
     g.W = W; g.ldw = K; g.w_rows = N;
     g.M = (int)T; g.N = N; g.K = K; g.K1 = K1;
@@ -68,6 +69,7 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
       ld = cout;
     }
     TcGemm g3;
+    g3.tmaps = h->tmaps;
     g3.A = a3; g3.lda = 128; g3.a_rows = T; g3.W = train ? w.kW3_h : w.kW3f_h; g3.ldw = 128; g3.w_rows = 256;
     g3.M = (int)T; g3.N = 256; g3.K = 128; g3.K1 = 128; g3.bias = train ? w.kb[3] : w.kbf[3]; g3.relu = train ? 0 : 1;
     g3.out_h = a4; g3.out_h_ld = 256;
@@ -78,6 +80,7 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
       SFM_TRY(bn_apply_relu<__nv_bfloat16>(a4, 256, 256, gr, b.bn_scale, b.bn_shift, st));
     }
     TcGemm g4;
+    g4.tmaps = h->tmaps;
     g4.A = a4; g4.lda = 256; g4.a_rows = T; g4.W = w.kW4_h; g4.ldw = 256; g4.w_rows = 256;
     g4.M = (int)T; g4.N = 256; g4.K = 256; g4.K1 = 256; g4.bias = w.kb[4];
     g4.out_h = b.xh; g4.out_h_ld = 256; g4.out_f = X; g4.out_f_ld = 256; g4.accumulate_f = 1;
@@ -86,8 +89,9 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
   const BnGroups gr{T0, T1, c.groups > 0 ? c.groups : 1};
   // fusion needs every statistic group to be whole 128-row GEMM tiles; ragged keypoint counts take the
   // stand-alone BatchNorm kernels
+  static const bool no_bn_fusion = getenv("SFM_NO_BN_FUSION") != nullptr;   // read once per process (A/B knob)
   const bool fuse_bn = train && T0 % gr.G == 0 && T1 % gr.G == 0 && (T0 / gr.G) % 128 == 0 && (T1 / gr.G) % 128 == 0 &&
-                       T0 > 0 && T1 > 0 && getenv("SFM_NO_BN_FUSION") == nullptr;
+                       T0 > 0 && T1 > 0 && !no_bn_fusion;
   for (int l = 0; l < 18; l++) {
     const SgLayer& L = w.L[l];
     const bool cross = l & 1;
@@ -95,12 +99,13 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
     {
       ProfScope ps(h, SFM_PROF_ATTENTION, st);
       TcAttn a;
+      a.tmaps = h->tmaps;
       a.qkv = b.qkv; a.rows_total = T; a.out = b.msgp; a.B = c.B;
       a.Nq[0] = c.K0; a.Nq[1] = c.K1;
       a.q_row0[0] = 0; a.q_row0[1] = T0;
       a.Nk[0] = cross ? c.K1 : c.K0; a.Nk[1] = cross ? c.K0 : c.K1;
       a.k_row0[0] = cross ? T0 : 0; a.k_row0[1] = cross ? 0 : T0;
-      SFM_TRY(tc_attention(a, st));
+      SFM_TRY(tc_attention(a, sms, st));
     }
     // the merge conv is folded into the MLP input weights (W1c), so the attention output feeds the MLP directly
     if (train && fuse_bn) {
@@ -109,6 +114,7 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
       {
         ProfScope ps(h, SFM_PROF_LINEAR, st);
         TcGemm g;
+        g.tmaps = h->tmaps;
         g.A = b.xh; g.lda = 256; g.A2 = b.msgp; g.lda2 = 256; g.a_rows = T;
         g.W = L.W1c_h; g.ldw = 512; g.w_rows = 512;
         g.M = (int)T; g.N = 512; g.K = 512; g.K1 = 256;
@@ -123,6 +129,7 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
       }
       ProfScope ps(h, SFM_PROF_LINEAR, st);
       TcGemm g;
+      g.tmaps = h->tmaps;
       g.A = b.hid; g.lda = 512; g.a_rows = T;
       g.W = L.W2_h; g.ldw = 512; g.w_rows = 256;
       g.M = (int)T; g.N = 256; g.K = 512; g.K1 = 512;
@@ -149,6 +156,7 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
   // scores_b = md0_b md1_b^T / 16  (superglue.py:264-265): batched, "weights" = the pair's side-1 descriptors
   ProfScope ps(h, SFM_PROF_LINEAR, st);
   TcGemm g;
+  g.tmaps = h->tmaps;
   g.A = b.mdh; g.lda = 256; g.a_rows = T; g.a_row_stride = c.K0;
   g.W = b.mdh; g.ldw = 256; g.w_rows = T; g.w_row_base = (int)T0; g.w_row_stride = c.K1;
   g.M = c.K0; g.N = c.K1; g.K = 256; g.K1 = 256; g.batch = c.B;

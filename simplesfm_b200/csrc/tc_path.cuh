@@ -23,6 +23,10 @@ int linear_f32_raw(const float* A, int lda, const float* A2, int lda2, int K1, c
 
 namespace tc {
 
+struct TmapCache;   // per-handle cache of encoded TMA tensor maps (tc_common.cuh)
+TmapCache* tmap_cache_create();
+void tmap_cache_destroy(TmapCache* c);
+
 // D_b[M,N] = alpha * A_b[M,K] * W_b[N,K]^T + bias   (bf16 operands, fp32 accumulation in TMEM)
 struct TcGemm {
   const __nv_bfloat16* A = nullptr;   // [a_rows, K1] row-major (lda)
@@ -57,7 +61,8 @@ struct TcGemm {
   int vec_f = 0, coalesced_rmw = 0, num_panels = 0, num_m_tiles = 0, cpp = 1;
   int dbg_flags = 0;
   int l2_prefetch = 2;   // bit 0: TMA-prefetch the next A tile into L2, bit 1: prefetch the next residual rows
-  long long* dbg = nullptr;  // optional per-role wait-cycle counters (SFM_TC_DEBUG)
+  long long* dbg = nullptr;  // optional per-role wait-cycle counters (debug builds, SFM_TC_DEBUG)
+  TmapCache* tmaps = nullptr;   // the handle's tensor-map cache (optional)
 };
 int tc_gemm(const TcGemm& p, int num_sms, cudaStream_t st);
 
@@ -72,8 +77,9 @@ struct TcAttn {
   int Nq[2] = {0, 0}, Nk[2] = {0, 0};
   long long q_row0[2] = {0, 0}, k_row0[2] = {0, 0};
   int stagger = 1;   // tile 1 of a CTA runs half a K/V step behind tile 0 (ping-pong on the MUFU pipe)
+  TmapCache* tmaps = nullptr;   // the handle's tensor-map cache (optional)
 };
-int tc_attention(const TcAttn& p, cudaStream_t st);
+int tc_attention(const TcAttn& p, int num_sms, cudaStream_t st);
 
 // 3x3 / pad 1 convolution, NHWC bf16, implicit GEMM on tcgen05 with 4-D TMA im2col (tc_conv.cu)
 struct TcConv {

@@ -74,24 +74,18 @@ def log_optimal_transport(scores: torch.Tensor, alpha, iters: int) -> torch.Tens
 
 
 def log_sinkhorn_iterations(Z: torch.Tensor, log_mu: torch.Tensor, log_nu: torch.Tensor, iters: int) -> torch.Tensor:
-    """ Perform Sinkhorn Normalization in Log-space for stability.
-    Supported for couplings of the form built by `log_optimal_transport` (constant dustbin row and
-    column, canonical marginals) -- the only way the reference calls it (superglue.py:170). """
-    b, m1, n1 = Z.shape
-    m, n = m1 - 1, n1 - 1
-    alpha = Z[0, -1, -1]
-    ok = bool((Z[:, -1, :] == alpha).all() and (Z[:, :, -1] == alpha).all())
-    norm = -math.log(m + n)
-    ref_mu = torch.full((m1,), norm, device=Z.device)
-    ref_mu[-1] = math.log(n) + norm
-    ref_nu = torch.full((n1,), norm, device=Z.device)
-    ref_nu[-1] = math.log(m) + norm
-    ok = ok and torch.allclose(log_mu, ref_mu.expand_as(log_mu), atol=1e-6) \
-        and torch.allclose(log_nu, ref_nu.expand_as(log_nu), atol=1e-6)
-    if not ok:
-        raise _lib.SfmError(-5, "log_sinkhorn_iterations: only dustbin-structured couplings are supported")
-    out = log_optimal_transport(Z[:, :-1, :-1].contiguous(), alpha, iters)
-    return out + norm          # log_optimal_transport subtracts `norm` at the end (superglue.py:170-171)
+    """ Perform Sinkhorn Normalization in Log-space for stability (superglue.py:142-148): any couplings
+    Z (b, m, n) and marginals log_mu (b, m), log_nu (b, n), CUDA f32 -> Z + u + v. """
+    z = require_cuda(Z, "Z", torch.float32)
+    b, m, n = z.shape
+    mu = require_cuda(log_mu, "log_mu", torch.float32).expand(b, m).contiguous()
+    nu = require_cuda(log_nu, "log_nu", torch.float32).expand(b, n).contiguous()
+    out = torch.empty_like(z)
+    ws = torch.empty(max(4 * b * (m + n), 256), dtype=torch.uint8, device=z.device)
+    with torch.cuda.device(z.device):
+        check(lib().sfm_log_sinkhorn_iterations(ptr(z), ptr(mu), ptr(nu), b, m, n, int(iters), ptr(out), ptr(ws),
+                                                ws.numel(), stream_ptr(z.device)))
+    return out
 
 
 class SuperGlue:

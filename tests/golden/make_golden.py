@@ -217,7 +217,72 @@ def golden_matcher():
     npz("matcher_images_e2e", **save)
 
 
+def golden_module_functions():
+    """Module-level functions the reference exports besides the classes (superpoint.py:27-39,
+    superglue.py:142-148,174-175) and `Matcher.match_datasets` (matcher.py:167-247) over the reference's own
+    `ImageFoldersDataset` (utils/datasets.py:16).  The JPEG files are stored byte for byte so that the GPU test
+    decodes exactly what the reference decoded."""
+    import io
+    from PIL import Image
+    from simple_sfm.utils.datasets import ImageFoldersDataset
+    g = torch.Generator().manual_seed(4321)
+    kp = torch.stack([torch.randint(0, 120, (400,), generator=g), torch.randint(0, 160, (400,), generator=g)], 1)
+    sc = torch.rand(400, generator=g)
+    rb_k, rb_s = RSP.remove_borders(kp, sc, 6, 120, 160)
+    tk_k, tk_s = RSP.top_k_keypoints(kp, sc, 123)
+    Z = torch.randn(2, 37, 53, generator=g) * 2
+    log_mu = torch.log_softmax(torch.randn(2, 37, generator=g), -1)
+    log_nu = torch.log_softmax(torch.randn(2, 53, generator=g), -1)
+    save = dict(rb_in_kpts=kp, rb_in_scores=sc, rb_border=np.int64(6), rb_h=np.int64(120), rb_w=np.int64(160),
+                rb_out_kpts=rb_k, rb_out_scores=rb_s, tk_k=np.int64(123), tk_out_kpts=tk_k, tk_out_scores=tk_s,
+                lsi_Z=Z, lsi_log_mu=log_mu, lsi_log_nu=log_nu,
+                lsi_out_25=RSG.log_sinkhorn_iterations(Z, log_mu, log_nu, 25),
+                lsi_out_0=RSG.log_sinkhorn_iterations(Z, log_mu, log_nu, 0),
+                arange_d0=RSG.arange_like(torch.zeros(3, 7, 5), 0), arange_d2=RSG.arange_like(torch.zeros(3, 7, 5), 2))
+    # ---- match_datasets: two folders (3 + 2 images) with masks, reference dataset class + reference Matcher
+    sp = S.save_state_dict(S.superpoint_state_dict(0), os.path.join(TMP, "sp.pth"))
+    sg = S.save_state_dict(S.superglue_state_dict(0, "indoor"), os.path.join(TMP, "sgi.pth"))
+
+    def grey(img):
+        return torch.from_numpy(np.asarray(img.convert("L"), dtype=np.float32) / 255.0)[None]
+
+    for masked in (False, True):
+        sets = []
+        tag = "md_masked" if masked else "md"
+        for d, seeds in (("a", (0, 1, 2)), ("b", (3, 4))):
+            rgb, msk = os.path.join(TMP, tag, d, "rgb"), os.path.join(TMP, tag, d, "mask")
+            os.makedirs(rgb)
+            os.makedirs(msk)
+            for i, sd in enumerate(seeds):
+                im = (S.textured_image(40 + (sd % 2), 120, 160, shift=(sd, 2 * sd))[0, 0] * 255).round().byte().numpy()
+                mk = np.zeros((120, 160), np.uint8)
+                mk[10:110, 20:150] = 255
+                for arr, folder, q in ((im, rgb, 95), (mk, msk, 100)):
+                    buf = io.BytesIO()
+                    Image.fromarray(arr, mode="L").save(buf, format="JPEG", quality=q)
+                    with open(os.path.join(folder, f"{d}{i:02d}.jpg"), "wb") as fh:
+                        fh.write(buf.getvalue())
+                    if not masked:
+                        save[f"jpg_{os.path.basename(folder)}_{d}{i:02d}"] = np.frombuffer(buf.getvalue(), np.uint8)
+            folders, tf = {"rgb": rgb}, {"rgb": grey}
+            if masked:
+                folders["mask"], tf["mask"] = msk, grey
+            sets.append(ImageFoldersDataset(folders, tf))
+        m = Matcher(sp, 4, 0.005, matcher_type="super_glue", super_glue_weights_path=sg,
+                    match_threshold=0.2, sinkhorn_iterations=20, super_glue_batch=2)
+        frames, table, names, split = m.match_datasets(sets, None, 1)
+        save[f"{tag}_names"] = np.array([names[i + 1] for i in range(len(names))])
+        save[f"{tag}_split"] = np.array(split)
+        for i, f in enumerate(frames):
+            save[f"{tag}_kpts_{i}"], save[f"{tag}_scores_{i}"] = f.keypoints_poses, f.scores
+            save[f"{tag}_image_shape_{i}"] = np.array(f.image.shape)
+        for (a, b), tb in table.items():
+            save[f"{tag}_table_{int(a)}_{int(b)}"] = tb
+    npz("module_functions", **save)
+
+
 if __name__ == "__main__":
-    golden_superpoint()
-    golden_superglue()
-    golden_matcher()
+    only = sys.argv[1:]
+    for fn in (golden_superpoint, golden_superglue, golden_matcher, golden_module_functions):
+        if not only or fn.__name__ in only:
+            fn()

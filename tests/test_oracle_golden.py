@@ -158,3 +158,20 @@ def test_colmap_payloads():
     assert np.array_equal(np.frombuffer(blob, np.float32).reshape(2, 4), [[1, 2, 1, 0], [3, 4, 1, 0]])
     pid, r, c, blob = O.colmap_match_blob(5, 2, np.array([[1, 9], [4, 8]], np.uint32))
     assert np.array_equal(np.frombuffer(blob, np.uint32).reshape(2, 2), [[9, 1], [8, 4]])
+
+
+def test_module_functions_golden():
+    """Oracle pieces behind the module-level functions the reference exports (superglue.py:142-148 with
+    arbitrary couplings; superpoint.py:27-39) against tests/golden/module_functions.npz."""
+    g = load_golden("module_functions")
+    Z, mu, nu = t(g["lsi_Z"]), t(g["lsi_log_mu"]), t(g["lsi_log_nu"])
+    u, v = O.log_sinkhorn(Z, mu, nu, 25)
+    torch.testing.assert_close(Z + u.unsqueeze(2) + v.unsqueeze(1), t(g["lsi_out_25"]), rtol=1e-5, atol=1e-5)
+    u0, v0 = O.log_sinkhorn(Z, mu, nu, 0)
+    assert torch.equal(Z + u0.unsqueeze(2) + v0.unsqueeze(1), t(g["lsi_out_0"]))
+    kp, sc = t(g["rb_in_kpts"]), t(g["rb_in_scores"])
+    b, h, w = int(g["rb_border"]), int(g["rb_h"]), int(g["rb_w"])
+    keep = (kp[:, 0] >= b) & (kp[:, 0] < h - b) & (kp[:, 1] >= b) & (kp[:, 1] < w - b)
+    assert torch.equal(kp[keep], t(g["rb_out_kpts"])) and torch.equal(sc[keep], t(g["rb_out_scores"]))
+    top = torch.topk(sc, int(g["tk_k"])).values
+    assert torch.equal(torch.sort(top).values, torch.sort(t(g["tk_out_scores"])).values)

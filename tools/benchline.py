@@ -1,6 +1,7 @@
-"""Condense bench.py JSON lines (stdin) to the handful of numbers compared between experiments."""
-import sys, json
-for l in sys.stdin:
+"""Condense bench.py JSON lines (files given as arguments, else stdin) to the handful of numbers compared
+between experiments."""
+import sys, json, fileinput
+for l in fileinput.input():
     l = l.strip()
     if l.startswith('{'):
         d = json.loads(l)
