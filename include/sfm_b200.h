@@ -195,6 +195,12 @@ SFM_API int sfm_tc_conv3x3(sfm_handle_t h, const void* in_nhwc, const void* w, c
 /* Matcher.__super_glue_matcher tail (matcher.py:103-109): per pair (L,2) uint32 rows
  * [i, matches0[i]] for matches0[i] > -1, in ascending i.  tables (B,K0,2) u32, lengths (B) i32. */
 SFM_API int sfm_compact_matches(const int64_t* matches0, int B, int K0, uint32_t* tables, int* lengths, void* stream);
+/* The same tables flattened for one device->host copy (and for the multi-GPU gather to the database writer's
+ * rank): rows [0, lengths[p]) of every pair's (kcap,2) table -> out (sum lengths, 2) u32 at row offsets[p]
+ * (exclusive prefix sum of lengths, int64).  The concatenation is what matcher.py:103-109 hands to
+ * colmap_bd_utils.py:354-367 pair by pair. */
+SFM_API int sfm_pack_tables(const uint32_t* tables, int n_pairs, int kcap, const int* lengths, const int64_t* offsets,
+                            uint32_t* out, void* stream);
 
 /* SimpleMatcher.match_two_way(_cuda) (simple_matcher.py:66-114): desc (256,N) / (256,M) unit f32.
  * out (3, min(N,M)) f32 rows [i, j, dist], count = L. */

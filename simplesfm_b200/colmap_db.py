@@ -11,8 +11,16 @@ fills it with exactly the payloads the reference writes:
     match.txt  "name1 name2" per pair                                           colmap_bd_utils.py:371-372
 
 Geometric verification (`colmap matches_importer`, `:374-381`) stays an external step: it is run only when a
-`colmap` executable is on PATH.  Method names mirror the reference class so that
-`generate_sparse_colmap` (`simple_sfm/dataset/simple_sfm_dataset_utils.py:129-139`) can use it unchanged.
+`colmap` executable is on PATH.  Method names mirror the reference class so that the three database calls of
+`generate_sparse_colmap` (`simple_sfm/dataset/simple_sfm_dataset_utils.py:129-139`) work unchanged; the COLMAP
+subprocess steps the reference class also exposes (`mapper`, `triangulation`, `run_mapper`;
+`colmap_bd_utils.py:94-147, 387-399`) are pass-throughs to the `colmap` executable and raise `FileNotFoundError`
+with a clear message when it is not installed.
+
+The shared camera (`--ImageReader.single_camera 1`, `:259`): when no size is given it is taken from the first
+image of `images_folder_path`, like `colmap feature_extractor` does -- width, height and
+f = 0.85 * max(w, h) (`default_focal_length_factor`, `:260`); with neither a size nor a readable image the
+constructor raises instead of guessing.
 """
 from __future__ import annotations
 
@@ -65,6 +73,7 @@ class ColmapDatabaseWriter(object):
         self.dense_path = os.path.join(db_dir, 'dense')
         self.db_path = os.path.join(db_dir, 'database.db')
         self.images_folder_path = images_folder_path
+        self.camera_type, self.camera_params = camera_type, camera_params
         os.makedirs(self.sparse_path, exist_ok=True)
         os.makedirs(self.dense_path, exist_ok=True)
         self.connection = sqlite3.connect(self.db_path)
@@ -74,7 +83,7 @@ class ColmapDatabaseWriter(object):
         self.connection.commit()
         if self.cursor.execute('SELECT COUNT(*) FROM cameras').fetchone()[0] == 0:
             # single shared camera, like `--ImageReader.single_camera 1` (colmap_bd_utils.py:259)
-            w, h = camera_size if camera_size is not None else (640, 480)
+            w, h = camera_size if camera_size is not None else self._first_image_size(images_folder_path)
             if camera_type is not None and camera_params is not None:
                 model, params, prior = CAMERA_MODELS[camera_type], np.asarray(camera_params, np.float64), 1
             else:   # default_focal_length_factor 0.85 (colmap_bd_utils.py:260), SIMPLE_RADIAL
@@ -82,6 +91,50 @@ class ColmapDatabaseWriter(object):
             self.cursor.execute('INSERT INTO cameras(camera_id, model, width, height, params, prior_focal_length) '
                                 'VALUES(1, ?, ?, ?, ?, ?);', (model, int(w), int(h), params.tobytes(), prior))
             self.connection.commit()
+
+    @staticmethod
+    def _first_image_size(folder: Optional[str]) -> Tuple[int, int]:
+        """(width, height) of the first image file in `folder` (name order), what `colmap feature_extractor`
+        would record for the shared camera."""
+        if folder is not None and os.path.isdir(folder):
+            from PIL import Image
+            for name in sorted(os.listdir(folder)):
+                if name.lower().endswith(('.png', '.jpg', '.jpeg', '.bmp', '.tif', '.tiff', '.ppm', '.pgm')):
+                    try:
+                        with Image.open(os.path.join(folder, name)) as im:
+                            return int(im.size[0]), int(im.size[1])
+                    except OSError:
+                        continue
+        raise ValueError('ColmapDatabaseWriter: the camera size is unknown -- pass camera_size=(width, height) or an '
+                         'images_folder_path that holds the images (the intrinsics written to the database decide '
+                         'geometric verification and triangulation)')
+
+    # ---- COLMAP subprocess steps of the reference class (colmap_bd_utils.py:94-147, 387-399): external binary
+    @staticmethod
+    def _colmap(args: List[str], check: bool = True):
+        if shutil.which('colmap') is None:
+            raise FileNotFoundError("the `colmap` executable is not on PATH: `colmap " + args[0] + "` is an external "
+                                    "step of the reference pipeline and is not reimplemented here")
+        subprocess.run(['colmap'] + args, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=check)
+
+    @classmethod
+    def mapper(cls, db_path, images_folder_path, sparse_path, camera_type=None, camera_params=None):
+        args = ['mapper', '--Mapper.ba_refine_principal_point', '1', '--Mapper.filter_max_reproj_error', '2',
+                '--Mapper.min_num_matches', '32', '--Mapper.extract_colors', '1', '--Mapper.max_num_models', '1',
+                '--database_path', db_path, '--image_path', images_folder_path, '--output_path', sparse_path]
+        if camera_type is not None and camera_params is not None:
+            args += ['--Mapper.ba_refine_focal_length', '1', '--Mapper.ba_refine_extra_params', '1',
+                     '--Mapper.ba_refine_principal_point', '1']
+        cls._colmap(args)
+
+    @classmethod
+    def triangulation(cls, db_path, images_folder_path, sparse_path, output_path):
+        cls._colmap(['point_triangulator', '--log_level', '1', '--Mapper.init_min_tri_angle', '4',
+                     '--Mapper.init_min_num_inliers', '25', '--database_path', db_path,
+                     '--image_path', images_folder_path, '--input_path', sparse_path, '--output_path', output_path])
+
+    def run_mapper(self):
+        self.mapper(self.db_path, self.images_folder_path, self.sparse_path, self.camera_type, self.camera_params)
 
     def close_bd(self):
         try:

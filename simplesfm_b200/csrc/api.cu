@@ -598,6 +598,13 @@ int sfm_compact_matches(const int64_t* matches0, int B, int K0, uint32_t* tables
   return compact_matches((const long long*)matches0, B, K0, tables, lengths, (cudaStream_t)stream);
 }
 
+int sfm_pack_tables(const uint32_t* tables, int n_pairs, int kcap, const int* lengths, const int64_t* offsets,
+                    uint32_t* out, void* stream) {
+  SFM_REQUIRE(n_pairs == 0 || (tables && lengths && offsets && out), "sfm_pack_tables: NULL argument");
+  SFM_REQUIRE(n_pairs >= 0 && kcap > 0, "sfm_pack_tables: bad dims");
+  return pack_tables(tables, n_pairs, kcap, lengths, (const long long*)offsets, out, (cudaStream_t)stream);
+}
+
 // ---- kernel-level test hooks of the tcgen05 path ------------------------------------------------
 int sfm_tc_gemm(sfm_handle_t h, const void* A, const void* A2, const void* W, int M, int N, int K, int K1,
                 const float* bias, float alpha, int relu, void* out_bf16, float* out_f32, int accumulate,

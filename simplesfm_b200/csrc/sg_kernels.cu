@@ -775,6 +775,18 @@ __global__ void __launch_bounds__(256) compact_kernel(const long long* __restric
   if (threadIdx.x == 0) lengths[b] = running;
 }
 
+// rows [0, lengths[p]) of every pair's (kcap, 2) table -> one flat (sum lengths, 2) array at offsets[p]
+__global__ void __launch_bounds__(256) pack_tables_kernel(const uint2* __restrict__ tables, int kcap,
+                                                          const int* __restrict__ lengths,
+                                                          const long long* __restrict__ offsets,
+                                                          uint2* __restrict__ out) {
+  const int p = blockIdx.x;
+  const int n = lengths[p];
+  const uint2* src = tables + (long long)p * kcap;
+  uint2* dst = out + offsets[p];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
 // SimpleMatcher: S <- -sqrt(2 - 2 clamp(S, -1, 1))   (simple_matcher.py:89-90; negated so argmax == argmin)
 __global__ void neg_l2_kernel(float* __restrict__ S, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1059,6 +1071,15 @@ int sinkhorn_write_Z(const SinkhornArgs& a, float* Z, cudaStream_t st) {
   const float norm = -logf((float)a.N + (float)a.M);
   dim3 grid(cdiv(a.M + 1, 256), a.N + 1, a.B);
   write_Z_kernel<<<grid, 256, 0, st>>>(a.S, a.N, a.M, a.alpha, a.u, a.v, norm, Z);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+int pack_tables(const unsigned* tables, int n_pairs, int kcap, const int* lengths, const long long* offsets,
+                unsigned* out, cudaStream_t st) {
+  if (n_pairs == 0) return SFM_OK;
+  pack_tables_kernel<<<n_pairs, 256, 0, st>>>(reinterpret_cast<const uint2*>(tables), kcap, lengths, offsets,
+                                              reinterpret_cast<uint2*>(out));
   SFM_LAUNCH_CHECK();
   return SFM_OK;
 }

@@ -66,5 +66,8 @@ int log_sinkhorn_general(const float* Z, const float* log_mu, const float* log_n
 
 // (L,2) uint32 match-table compaction per pair: rows [i, matches0[i]] for matches0[i] > -1
 int compact_matches(const long long* matches0, int B, int N, unsigned* tables, int* lengths, cudaStream_t st);
+// flatten per-pair (kcap, 2) tables into one (sum lengths, 2) array; offsets = exclusive prefix sum of lengths
+int pack_tables(const unsigned* tables, int n_pairs, int kcap, const int* lengths, const long long* offsets,
+                unsigned* out, cudaStream_t st);
 
 }  // namespace sfm

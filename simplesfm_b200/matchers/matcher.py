@@ -2,8 +2,10 @@
 
 Same class, constructor arguments, methods and return values as the reference `Matcher`
 (matcher.py:31-400) and the same `Frame` tuple (matcher.py:24-28).  Differences are additive
-only: `max_keypoints`, `bn_mode`, `precision`, `device` keyword arguments, and pair sharding
-across ranks when `torch.distributed` is initialised (`shard_pairs=True`).
+only: `max_keypoints`, `bn_mode`, `precision`, `device` keyword arguments, and -- opt-in with
+`shard_pairs=True` on an initialised `torch.distributed` process group -- the multi-GPU partition of
+SURVEY.md 8e: images dealt to the ranks for SuperPoint, one all-gather of the feature records, the pair
+list cut into chunk-aligned ranges, compact match tables gathered to rank 0 (`distributed.py`).
 
 The SuperGlue hot loop keeps the reference semantics -- consecutive chunks of `super_glue_batch`
 pairs, every side truncated to the chunk-minimum keypoint count (matcher.py:73-91), `(L,2)`
@@ -58,6 +60,20 @@ class FeatureStore:
                 self.kpts[i, :k].copy_(f.keypoints_poses, non_blocking=True)
                 self.scores[i, :k].copy_(f.scores, non_blocking=True)
 
+    @classmethod
+    def from_records(cls, rec) -> "FeatureStore":
+        """Adopt gathered records (`distributed.Records`) without copying them again."""
+        self = cls.__new__(cls)
+        self.desc, self.kpts, self.scores = rec.desc, rec.kpts, rec.scores
+        self.counts, self.hw, self.kcap = list(rec.counts), list(rec.hw), int(rec.desc.shape[-1])
+        return self
+
+
+class FrameList(list):
+    """`List[Frame]` whose frames are views into one `FeatureStore` (what the image sources return when the
+    features were all-gathered): `_super_glue_matcher` then matches straight from the store."""
+    store: FeatureStore = None
+
 
 class Matcher(object):
 
@@ -74,15 +90,24 @@ class Matcher(object):
                  bn_mode: str = 'train',
                  precision: str = 'fp32',
                  device: str = 'cuda',
-                 shard_pairs: bool = True,
+                 shard_pairs: bool = False,
                  fuse_chunks: int = 32,
                  superpoint_precision: str = 'fp32',
                  extract_batch: int = 8,
-                 decode_threads: int = 4):
+                 decode_threads: int = 4,
+                 process_group=None,
+                 gather_tables: str = 'root'):
 
         self.matcher_type = matcher_type
         self.device = torch.device(device)
-        self.shard_pairs = shard_pairs
+        # multi-GPU (opt-in): every rank must call the image sources / match_frames with the SAME scene.
+        # `gather_tables`: 'root' = rank 0 returns the table of every pair, the other ranks only their own pairs
+        # (rank 0 is the database writer); 'none' = every rank keeps only its own pairs.
+        self.shard_pairs = bool(shard_pairs)
+        self.process_group = process_group
+        if gather_tables not in ('root', 'none'):
+            raise ValueError("gather_tables must be 'root' or 'none'")
+        self.gather_tables = gather_tables
         # consecutive chunks with identical keypoint counts are launched together (better GPU occupancy);
         # BatchNorm statistics stay per chunk, so results equal the chunk-by-chunk loop of the reference
         self.fuse_chunks = max(1, int(fuse_chunks)) if precision == 'bf16' else 1
@@ -120,38 +145,60 @@ class Matcher(object):
         :return: Dict where the key is a pair from the match_list,
                 and the value is the points that match between images in pair.
         """
-        match_table = {}
+        return self._super_glue_tables(frames, match_list, super_chunk).to_dict()
+
+    def _super_glue_tables(self, frames: List[Frame], match_list: np.ndarray, super_chunk: int = 2048):
+        """The hot loop (matcher.py:60-113) with compact output: `distributed.CompactTables` (pairs, per-pair
+        lengths, all rows concatenated) -- no per-pair host object until `to_dict()`."""
+        from ..distributed import CompactTables, concat_tables
+        match_list = np.asarray(match_list, dtype=np.int64).reshape(-1, 2)
         if len(match_list) == 0:
-            return match_table
+            return concat_tables([])
         sg: SuperGlue = self.matcher
         dev = sg.device
-        store = FeatureStore(frames, dev)
+        store = getattr(frames, 'store', None) or FeatureStore(frames, dev)
         pairs0 = np.ascontiguousarray(match_list - 1)
         idx0_all = torch.from_numpy(np.ascontiguousarray(pairs0[:, 0]).astype(np.int32)).to(dev)
         idx1_all = torch.from_numpy(np.ascontiguousarray(pairs0[:, 1]).astype(np.int32)).to(dev)
         bs = int(self.super_glue_batch)
         P = len(pairs0)
         L = lib()
+        counts = np.asarray(store.counts, dtype=np.int64)
+        uniform_hw = len(set(store.hw)) == 1
         super_chunk = max(bs, super_chunk // bs * bs)
         # chunks per launch: bounded so that one launch holds at most 256 pairs (score matrices + activations of a
         # launch at 4096 keypoints stay around 35 GB)
         fuse_limit = max(1, min(self.fuse_chunks, 256 // bs))
+        parts = []
         for s0 in range(0, P, super_chunk):
             s1 = min(P, s0 + super_chunk)
             n_sc = s1 - s0
             tables = torch.empty(n_sc, store.kcap, 2, dtype=torch.int32, device=dev)
             lengths = torch.zeros(n_sc, dtype=torch.int32, device=dev)
+            # chunk-minimum keypoint counts of both sides (matcher.py:82-83), all chunks of the super-chunk at once
+            n_ch = (n_sc + bs - 1) // bs
+            pad = n_ch * bs - n_sc
+            c0s = counts[pairs0[s0:s1, 0]]
+            c1s = counts[pairs0[s0:s1, 1]]
+            if pad:
+                c0s = np.concatenate([c0s, np.full(pad, c0s[-1])])
+                c1s = np.concatenate([c1s, np.full(pad, c1s[-1])])
+            k0s = c0s.reshape(n_ch, bs).min(1)
+            k1s = c1s.reshape(n_ch, bs).min(1)
             # plan: (first pair, number of pairs, k0, k1, hw0, hw1, fused chunk count)
             plan = []
-            for c0 in range(s0, s1, bs):
+            for ci, c0 in enumerate(range(s0, s1, bs)):
                 c1 = min(s1, c0 + bs)
-                k0 = min(store.counts[i] for i in pairs0[c0:c1, 0])      # matcher.py:82
-                k1 = min(store.counts[i] for i in pairs0[c0:c1, 1])      # matcher.py:83
-                hw0 = {store.hw[i] for i in pairs0[c0:c1, 0]}
-                hw1 = {store.hw[i] for i in pairs0[c0:c1, 1]}
-                if len(hw0) != 1 or len(hw1) != 1:
-                    raise RuntimeError("stack expects each tensor to be equal size (images of one chunk differ)")
-                key = (k0, k1, next(iter(hw0)), next(iter(hw1)))
+                k0, k1 = int(k0s[ci]), int(k1s[ci])
+                if uniform_hw:
+                    h0 = h1 = store.hw[0]
+                else:
+                    hw0 = {store.hw[i] for i in pairs0[c0:c1, 0]}
+                    hw1 = {store.hw[i] for i in pairs0[c0:c1, 1]}
+                    if len(hw0) != 1 or len(hw1) != 1:
+                        raise RuntimeError("stack expects each tensor to be equal size (images of one chunk differ)")
+                    h0, h1 = next(iter(hw0)), next(iter(hw1))
+                key = (k0, k1, h0, h1)
                 full = (c1 - c0) == bs
                 if (plan and full and tuple(plan[-1][2:6]) == key and plan[-1][6] < fuse_limit
                         and plan[-1][1] == plan[-1][6] * bs):
@@ -177,33 +224,46 @@ class Matcher(object):
                                                 stream_ptr(dev)))
                 if dst is not tview:
                     tview[:, :k0].copy_(dst)
-            lens = lengths.cpu().numpy()                                    # one sync per super-chunk
-            maxlen = int(lens.max()) if n_sc else 0
-            host = tables[:, :max(maxlen, 1)].cpu().numpy().view(np.uint32)
-            for p in range(n_sc):
-                a, b = pairs0[s0 + p]
-                match_table[(a + 1, b + 1)] = host[p, :lens[p]].copy()
-        return match_table
+            # flatten on the device, then ONE device->host copy of exactly the rows that exist
+            ends = torch.cumsum(lengths, 0, dtype=torch.int64)
+            offsets = ends - lengths
+            lens_host = lengths.cpu().numpy().astype(np.int64)              # the one sync per super-chunk
+            total = int(lens_host.sum())
+            flat = torch.empty(max(total, 1), 2, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                check(L.sfm_pack_tables(ptr(tables), n_sc, store.kcap, ptr(lengths), ptr(offsets), ptr(flat),
+                                        stream_ptr(dev)))
+            rows = flat[:total].cpu().numpy().view(np.uint32)
+            parts.append(CompactTables(match_list[s0:s1], lens_host, rows))
+        return concat_tables(parts)
 
     def _simple_matcher(self, frames: List[Frame], match_list: np.ndarray) -> Dict[Tuple[int, int], np.array]:
         """Mutual nearest-neighbour tables (matcher.py:115-131): per pair the first two rows of
         `match_two_way_cuda` ([index0, index1, distance]) as an (L, 2) uint32 array."""
-        table = {}
+        return self._simple_tables(frames, match_list).to_dict()
+
+    def _simple_tables(self, frames: List[Frame], match_list: np.ndarray):
+        from ..distributed import CompactTables, concat_tables
+        match_list = np.asarray(match_list, dtype=np.int64).reshape(-1, 2)
+        if len(match_list) == 0:
+            return concat_tables([])
         nn = self.matcher
-        for a, b in match_list:
-            triple = nn.match_two_way_cuda(frames[a - 1].descriptors, frames[b - 1].descriptors)
-            table[(a, b)] = triple[:2].t().cpu().numpy().astype(np.uint32)
-        return table
+        rows, lens = nn.match_pairs([f.descriptors for f in frames], match_list - 1)
+        return CompactTables(match_list, lens, rows)
+
+    def _group(self):
+        """(process group, rank, world) of the opt-in multi-GPU mode, (None, 0, 1) otherwise."""
+        from ..distributed import active_group
+        return active_group(self.shard_pairs, self.process_group)
 
     def _shard(self, match_list: np.ndarray) -> np.ndarray:
         """Contiguous, chunk-aligned slice of the pair list for this rank (SURVEY.md 8e phase 3).
         Chunk alignment keeps train-mode BatchNorm statistics identical to a single-GPU run."""
-        import torch.distributed as dist
-        if not (self.shard_pairs and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        group, rank, world = self._group()
+        if group is None:
             return match_list
         from ..distributed import shard_range
-        bs = getattr(self, 'super_glue_batch', 1)
-        lo, hi = shard_range(len(match_list), bs, dist.get_rank(), dist.get_world_size())
+        lo, hi = shard_range(len(match_list), getattr(self, 'super_glue_batch', 1), rank, world)
         return match_list[lo:hi]
 
     @staticmethod
@@ -249,27 +309,62 @@ class Matcher(object):
         t0 = time.time()
         logger.info('Starts matching descriptors.')
         wanted = self.pair_list(list(images_names.keys()), match_pairs_filter)
+        group, rank, world = self._group()
+        if group is not None:     # every rank must hold the same scene
+            from ..distributed import assert_same_everywhere
+            assert_same_everywhere([len(frames), len(wanted), sum(int(f.keypoints_poses.shape[0]) for f in frames)],
+                                   self.device, group, what="frames / pair list")
         mine = self._shard(wanted)
-        run = {'simple': self._simple_matcher, 'super_glue': self._super_glue_matcher}.get(self.matcher_type)
-        match_table = run(frames, mine) if run is not None else None
-        if mine is not wanted:      # every rank returns the full, identically ordered table
-            from ..distributed import gather_match_tables
-            match_table = gather_match_tables(match_table, wanted)
+        if self.matcher_type == 'super_glue':
+            tables = self._super_glue_tables(frames, mine)
+        elif self.matcher_type == 'simple':
+            tables = self._simple_tables(frames, mine)
+        else:
+            tables = None
+        if tables is None:
+            match_table = None
+        else:
+            if group is not None and self.gather_tables == 'root':
+                # compact uint32 rows + lengths to rank 0 (the database writer); other ranks keep their own pairs
+                from ..distributed import gather_tables_to_root
+                merged = gather_tables_to_root(tables, wanted, getattr(self, 'super_glue_batch', 1), self.device, group)
+                tables = merged if merged is not None else tables
+            match_table = tables.to_dict()
         self._report('matching', time.time() - t0, num_matches=len(wanted),
-                     num_matched_points=sum(len(v) for v in match_table.values()))
+                     num_matched_points=0 if match_table is None else sum(len(v) for v in match_table.values()))
         return frames, match_table, images_names
 
     # ------------------------------------------------------------------------------------------
     # image sources (matcher.py:167-400).  All three feed one ingestion pipeline (ingest.py): host decode runs ahead
     # on `decode_threads` threads, pixels go up as they are, SuperPoint runs `extract_batch` images at a time;
     # image ids are 1-based in arrival order, exactly like the reference's per-image loops.
-    def _frames_from(self, items) -> List[Frame]:
-        """items: iterable of (grey image (H, W) u8 | f32 host array, mask host array | None)."""
+    def _frames_from(self, items, presharded: bool = False) -> List[Frame]:
+        """items: iterable of (grey image (H, W) u8 | f32 host array, mask host array | None) over ALL images of the
+        scene, in image-id order.  In the multi-GPU mode rank r extracts images r, r + G, r + 2G, ... only
+        (`presharded=True`: `items` already holds just this rank's images) and one all-gather hands every rank the
+        features of every image (SURVEY.md 8e phases 1-2); the frames are then views into the gathered records."""
         from ..ingest import FrameExtractor
         t0 = time.time()
         logger.info('Starts extracting descriptors.')
+        group, rank, world = self._group()
+        if group is not None and not presharded:
+            items = (it for i, it in enumerate(items) if i % world == rank)
         ex = FrameExtractor(self.super_point_extractor, self.extract_batch)
-        frames = [Frame(e.descriptors, e.keypoints, e.scores, e.image) for e in ex.extract(items)]
+        extracted = ex.extract(items)
+        if group is None:
+            frames = [Frame(e.descriptors, e.keypoints, e.scores, e.image) for e in extracted]
+        else:
+            from ..distributed import allgather_records
+            rec = allgather_records([(e.descriptors, e.keypoints, e.scores, tuple(e.image.shape[-2:]))
+                                     for e in extracted], None, self.device, group)
+            frames = FrameList()
+            frames.store = FeatureStore.from_records(rec)
+            blank = torch.zeros((), dtype=torch.float32, device=self.device)
+            for i, (k, hw) in enumerate(zip(rec.counts, rec.hw)):
+                # the image itself stays on the rank that decoded it; elsewhere only its SHAPE is needed
+                # (superglue.py:250-251), carried by a zero-stride view
+                image = extracted[i // world].image if i % world == rank else blank.expand(1, hw[0], hw[1])
+                frames.append(Frame(rec.desc[i, :, :k], rec.kpts[i, :k], rec.scores[i, :k], image))
         self._report('extraction', time.time() - t0, num_images=len(frames),
                      num_keypoints=sum(len(f.keypoints_poses) for f in frames))
         return frames
@@ -343,5 +438,7 @@ class Matcher(object):
             return read
 
         names = {i + 1: e['file_path'].split('/')[-1] for i, e in enumerate(entries)}
-        frames = self._frames_from(decode_ahead([reader(e) for e in entries], self.decode_threads))
+        _, rank, world = self._group()
+        loaders = [reader(e) for e in entries][rank::world]      # this rank decodes only the images it extracts
+        frames = self._frames_from(decode_ahead(loaders, self.decode_threads), presharded=True)
         return self.match_frames(frames, names, match_pairs_filter)

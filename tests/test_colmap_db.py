@@ -41,3 +41,32 @@ def test_colmap_writer_roundtrip(tmp_path):
     assert open(os.path.join(str(tmp_path), "match.txt")).read() == "c.png a.png\n"
     assert db.image_ids_to_pair_id(5, 2) == 2 * 2147483647 + 5 == O.colmap_pair_id(5, 2)
     assert con.execute("SELECT model, width, height FROM cameras").fetchall() == [(2, 640, 480)]
+
+
+def test_camera_from_first_image_and_external_steps(tmp_path):
+    """Without an explicit size the shared camera comes from the first image file (what `colmap feature_extractor`
+    records, colmap_bd_utils.py:256-273): width, height, f = 0.85 * max(w, h); without any size the writer raises.
+    The COLMAP subprocess steps are pass-throughs that fail loudly when the binary is missing."""
+    import shutil
+    import sqlite3
+    import pytest
+    from PIL import Image
+    from simplesfm_b200.colmap_db import ColmapDatabaseWriter
+    imgs = tmp_path / "images"
+    imgs.mkdir()
+    Image.fromarray(np.zeros((300, 500), np.uint8)).save(imgs / "b.png")
+    Image.fromarray(np.zeros((360, 720), np.uint8)).save(imgs / "a.png")       # first in name order
+    db = ColmapDatabaseWriter(str(tmp_path / "colmap"), images_folder_path=str(imgs))
+    con = sqlite3.connect(str(tmp_path / "colmap" / "database.db"))
+    model, w, h, params, prior = con.execute("SELECT model, width, height, params, prior_focal_length FROM cameras").fetchone()
+    assert (model, w, h, prior) == (2, 720, 360, 0)
+    assert np.frombuffer(params, np.float64).tolist() == [0.85 * 720, 360.0, 180.0, 0.0]
+    with pytest.raises(ValueError):
+        ColmapDatabaseWriter(str(tmp_path / "colmap2"))
+    with pytest.raises(ValueError):
+        ColmapDatabaseWriter(str(tmp_path / "colmap3"), images_folder_path=str(tmp_path / "missing"))
+    if shutil.which("colmap") is None:
+        with pytest.raises(FileNotFoundError):
+            db.triangulation(db.db_path, str(imgs), db.sparse_path, db.sparse_path)
+        with pytest.raises(FileNotFoundError):
+            db.run_mapper()

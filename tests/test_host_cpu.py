@@ -127,29 +127,63 @@ def _free_port():
 def _gloo_worker(rank, world, port, out):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
-    from simplesfm_b200.distributed import allgather_feature_records, gather_match_tables, image_block, shard_range
+    from simplesfm_b200.distributed import (CompactTables, active_group, allgather_records, assert_same_everywhere,
+                                            concat_tables, gather_tables_to_root, shard_range)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
+        cpu = torch.device("cpu")
+        group, r, w = active_group(True)
+        ok = (r, w) == (rank, world) and active_group(False) == (None, 0, 1)
+        # ---- phase 4: compact tables of this rank's chunk-aligned pair range -> rank 0 only
         ids = list(range(1, 8))
-        pairs = np.array([(a, b) for i, a in enumerate(ids) for b in ids[i + 1:]])
+        pairs = np.array([(a, b) for i, a in enumerate(ids) for b in ids[i + 1:]], dtype=np.int64)
         lo, hi = shard_range(len(pairs), 4, rank, world)
         rng = np.random.RandomState(0)
         full = {(np.int64(a), np.int64(b)): rng.randint(0, 500, size=(int(a * 3 + b) % 9, 2)).astype(np.uint32)
                 for a, b in pairs}
-        local = {k: full[k] for k in list(full)[lo:hi]}
-        merged = gather_match_tables(local, pairs)
-        ok = list(merged.keys()) == list(full.keys()) and all(np.array_equal(merged[k], full[k]) and
-                                                              merged[k].dtype == np.uint32 for k in full)
-        # feature records: each rank owns a block of images
-        n_img, kcap = 5, 6
+        keys = list(full)
+        local = CompactTables(pairs[lo:hi], np.array([len(full[k]) for k in keys[lo:hi]], dtype=np.int64),
+                              np.concatenate([full[k] for k in keys[lo:hi]]).reshape(-1, 2))
+        merged = gather_tables_to_root(local, pairs, 4, cpu, group)
+        if rank == 0:
+            table = merged.to_dict()
+            ok = ok and list(table.keys()) == keys and all(np.array_equal(table[k], full[k]) and
+                                                           table[k].dtype == np.uint32 for k in full)
+            ok = ok and all(isinstance(k[0], np.int64) for k in table)
+        else:
+            ok = ok and merged is None
+        # an empty shard (fewer chunks than ranks) still takes part in the collectives
+        tiny = pairs[:3]
+        lo, hi = shard_range(len(tiny), 4, rank, world)
+        loc = CompactTables(tiny[lo:hi], np.array([len(full[k]) for k in keys[:3]][lo:hi], dtype=np.int64),
+                            (np.concatenate([full[k] for k in keys[:3]]) if hi > lo else np.zeros((0, 2), np.uint32)
+                             ).reshape(-1, 2))
+        merged = gather_tables_to_root(loc, tiny, 4, cpu, group)
+        if rank == 0:
+            t3 = merged.to_dict()
+            ok = ok and list(t3.keys()) == keys[:3] and all(np.array_equal(t3[k], full[k]) for k in keys[:3])
+        ok = ok and concat_tables([]).to_dict() == {}
+        # ---- phase 2: rank r owns images r, r + world, ...; ragged keypoint counts, mixed image sizes
+        n_img = 5
         g = torch.Generator().manual_seed(1)
-        desc = torch.randn(n_img, 256, kcap, generator=g)
-        kp = torch.randn(n_img, kcap, 2, generator=g)
-        sc = torch.rand(n_img, kcap, generator=g)
-        cnt = torch.arange(n_img, dtype=torch.int32) + 1
-        a, b = image_block(n_img, rank, world)
-        d2, k2, s2, c2 = allgather_feature_records(desc[a:b], kp[a:b], sc[a:b], cnt[a:b], n_img)
-        ok = ok and torch.equal(d2, desc) and torch.equal(k2, kp) and torch.equal(s2, sc) and torch.equal(c2, cnt)
+        counts = [6, 0, 3, 5, 1]
+        hw = [(480, 640), (480, 640), (240, 320), (480, 640), (120, 160)]
+        desc = [torch.randn(256, k, generator=g) for k in counts]
+        kp = [torch.randn(k, 2, generator=g) for k in counts]
+        sc = [torch.rand(k, generator=g) for k in counts]
+        mine = [(desc[i], kp[i], sc[i], hw[i]) for i in range(rank, n_img, world)]
+        rec = allgather_records(mine, None, cpu, group)
+        ok = ok and rec.counts == counts and rec.hw == hw and rec.desc.shape == (n_img, 256, 8)
+        for i, k in enumerate(counts):
+            ok = ok and torch.equal(rec.desc[i, :, :k], desc[i]) and torch.equal(rec.kpts[i, :k], kp[i]) \
+                and torch.equal(rec.scores[i, :k], sc[i])
+        # ---- ranks handed different scenes are detected
+        assert_same_everywhere([n_img, len(pairs)], cpu, group)
+        try:
+            assert_same_everywhere([n_img + rank], cpu, group)
+            ok = False
+        except RuntimeError:
+            pass
         out.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -167,6 +201,17 @@ def test_gloo_world2_gather_tables_and_features():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_compact_tables_roundtrip():
+    from simplesfm_b200.distributed import CompactTables, concat_tables
+    a = CompactTables(np.array([[1, 2], [1, 3]], np.int64), np.array([2, 0], np.int64),
+                      np.array([[0, 5], [3, 1]], np.uint32))
+    b = CompactTables(np.array([[2, 3]], np.int64), np.array([1], np.int64), np.array([[7, 7]], np.uint32))
+    d = concat_tables([a, b]).to_dict()
+    assert list(d.keys()) == [(1, 2), (1, 3), (2, 3)]
+    assert d[(1, 2)].tolist() == [[0, 5], [3, 1]] and d[(1, 3)].shape == (0, 2) and d[(2, 3)].tolist() == [[7, 7]]
+    assert all(v.dtype == np.uint32 for v in d.values())
 
 
 def test_pair_list_matches_itertools_and_vectorised_filters():
