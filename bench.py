@@ -311,6 +311,18 @@ def run_ours(a):
     sub_names = {i + 1: names[i + 1] for i in range(sub_n)}
     sub_table = table if sub_n == n_img else m.match_frames(resident[:sub_n], sub_names, None)[1]
     sha = table_hash(sub_table) if rank == 0 else None
+    sharded_equals_single = None
+    if world > 1:
+        # direct check on rank 0: the same 50-image scene matched WITHOUT sharding on this GPU
+        if rank == 0:
+            solo = make_matcher(shard=False).match_frames(resident[:sub_n], sub_names, None)[1]
+            bad = [k for k in solo if k not in sub_table or not np.array_equal(solo[k], sub_table[k])]
+            sharded_equals_single = len(bad) == 0 and len(solo) == len(sub_table)
+            if bad:
+                print(f"bench.py: {len(bad)} of {len(solo)} pairs differ between the sharded and the single-GPU run, "
+                      f"first {bad[:3]} ({[(len(solo[k]), len(sub_table.get(k, []))) for k in bad[:3]]})", file=sys.stderr)
+            sha_single = table_hash(solo)
+        barrier()
 
     # ---- roofline of the dominant kernel (attention), from this rank's launches
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -390,7 +402,8 @@ def run_ours(a):
             "gflop_per_pair": 254.8 if a.kp == 2048 else None,
             "tensor_frac_whole_step": (value / world * 254.8e9 / 1e12) / peak if a.kp == 2048 else None,
             "matches_per_step": int(sum(len(v) for v in table.values())) if rank == 0 else None,
-            "table_sha256_50_image_scene": sha, "parity": parity}
+            "table_sha256_50_image_scene": sha, "sharded_table_equals_single_gpu": sharded_equals_single,
+            "parity": parity}
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
     if not a.no_configs:

@@ -69,7 +69,15 @@ def superglue_state_dict(seed: int = 0, variant: str = "indoor") -> Dict[str, to
         conv(p + ".mlp.3", 512, 256, gain=0.04, zero_bias=True)
     # final projection: a scaled random orthogonal map keeps descriptor similarity so that
     # related keypoints score high (scores = <m0, m1> / 16)
-    q, _ = torch.linalg.qr(torch.randn(256, 256, generator=g))
+    # LAPACK's QR rounds differently for different thread counts (observed: 1 thread vs 8 differ by 1e-5), and
+    # torchrun starts every rank with OMP_NUM_THREADS=1: pin the count the golden vectors were generated with, so
+    # that every process -- tests, bench ranks, golden script -- builds bit-identical weights
+    n_threads = torch.get_num_threads()
+    torch.set_num_threads(8)
+    try:
+        q, _ = torch.linalg.qr(torch.randn(256, 256, generator=g))
+    finally:
+        torch.set_num_threads(n_threads)
     sd["final_proj.weight"] = (q * 10.0)[:, :, None].contiguous()
     sd["final_proj.bias"] = torch.randn(256, generator=g) * 0.05
     return sd
