@@ -14,7 +14,8 @@ from typing import Dict, Optional
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsfm_b200.so")
+# SFM_LIB selects another build of the same library (A/B timing of kernel variants); the default is the in-tree build
+LIB_PATH = os.environ.get("SFM_LIB") or os.path.join(HERE, "libsfm_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "sfm_b200.h")
 
 BN_TRAIN, BN_EVAL = 0, 1

@@ -153,6 +153,17 @@ int sfm_create(int device, sfm_handle_t* out) {
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   h->tmaps = tc::tmap_cache_create();
+  {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, tc::att_redo_bytes());
+    if (e == cudaSuccess) e = cudaMemset(p, 0, tc::att_redo_bytes());
+    if (e != cudaSuccess) {
+      delete h;
+      return cuda_fail(e, "cudaMalloc(attention redo list)", __FILE__, __LINE__);
+    }
+    h->att_redo = (int*)p;
+    h->allocs.push_back(p);
+  }
   *out = h;
   return SFM_OK;
 }
@@ -631,6 +642,7 @@ int sfm_tc_attention(sfm_handle_t h, const void* qkv, long long rows_total, int 
   a.Nq[0] = Nq0; a.Nk[0] = Nk0; a.q_row0[0] = q_row0_0; a.k_row0[0] = k_row0_0;
   a.Nq[1] = Nq1; a.Nk[1] = Nk1; a.q_row0[1] = q_row0_1; a.k_row0[1] = k_row0_1;
   a.tmaps = h->tmaps;
+  a.redo = h->att_redo; a.redo_cap = tc::ATT_REDO_CAP;
   return tc::tc_attention(a, h->sm_count, (cudaStream_t)stream);
 }
 

@@ -65,6 +65,7 @@ namespace sfm { namespace tc { struct TmapCache; } }
 struct sfm_ctx {
   int device = 0;
   sfm::tc::TmapCache* tmaps = nullptr;   // encoded TMA tensor maps of this handle's launches
+  int* att_redo = nullptr;               // attention rows handed to the exact recomputation (tc_attention.cu)
   int sm_count = 148;
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[SFM_PROF_KINDS];  // recorded this window

@@ -11,9 +11,19 @@
 //                O_t = P_t V_j  (A = P from TMEM)
 //   warps 3-6  : softmax warpgroup of tile 0 (thread = query row), warps 7-10: tile 1
 // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512)
-// O accumulates in TMEM across K/V tiles.  The softmax threads keep a (possibly stale) reference
-// maximum per row and only rescale O / the running sum when the true maximum has grown by more
-// than 2^8 (lazy rescale: probabilities stay <= 256, exact after the final division by the sum).
+// O accumulates in TMEM across K/V tiles.  The softmax threads exponentiate a step relative to the row maximum
+// of the steps BEFORE it (one step of lag) and move that reference only when the running maximum has grown by
+// more than 2^8 -- probabilities stay far inside the exponent range of bf16 / fp32 and the result is exact after
+// the final division by the sum.  Because nothing about a step's scores has to be known before its first
+// exponential, S streams from TMEM in 32-column chunks and loads, maxima and MUFU work overlap.
+//
+// What bounds the kernel (profiles/README.md, round 2): the arithmetic of a step -- 128 x (FFMA, MUFU.EX2, FADD),
+// 64 F2FP, 64 FMNMX3 per row -- runs at the MUFU rate (16 ex2 / clk / SM; tools/micro/exp_mix_bench.cu), i.e.
+// 2 x 1 045 clocks per K/V step for the two softmax warps of a scheduler.  The kernel needs about 2 900: the
+// remainder is synchronisation latency (mbarrier waits, TMEM load / store round trips, the unit epilogue) that
+// two warps per scheduler cannot hide from each other.  Measured and NOT helpful: a start offset between the
+// tiles (any offset random-walks away), strict MUFU turn-taking between the paired warps (their bubbles end up
+// serialised), PRMT instead of F2FP packing, separate issue threads alone.
 #include "tc_common.cuh"
 #include "tc_path.cuh"
 #include <stdlib.h>
@@ -60,11 +70,7 @@ __device__ __forceinline__ Unit decode_unit(const TcAttn& p, int u, int units0, 
   return w;
 }
 
-// DBG != 0 only exists in -DSFM_ATT_EXPERIMENTS builds (tools/att_experiments.sh): it removes one stage of the
-// softmax loop at a time to measure what that stage costs (results are then meaningless):
-//   1 no MUFU (FFMA instead of ex2)   2 S is loaded from TMEM only on a unit's first step   4 no P store
-//   8 no row-sum adds   16 no row maximum
-template <int NT, int DBG = 0>
+template <int NT>
 __global__ void __launch_bounds__(AttCfg<NT>::THREADS, 1)
 tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units0, int qt0, int qt1, int n_units) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -199,100 +205,120 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     const float c = 0.125f * 1.4426950408889634f;  // log2(e) / sqrt(64)
     int g = 0;
-    // tile 1 starts after tile 0 has produced its first probability tile: half a step of lag (see the issuer)
+    // tile 1 starts after tile 0 has produced its first probability tile: half a step of lag
     if (NT > 1 && t == 1 && p.stagger) mbar_wait(&bars->p_full[0], 0);
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
     const Unit w = decode_unit<NT>(p, u, units0, qt0, qt1);
     const int Nk = w.Nk, n_kv = w.n_kv;
     const int qi = w.qblk * (NT * 128) + t * 128 + row_in_tile;  // query index inside the pair
-    float m_used = -INFINITY, l_run = 0.f;
+    // Reference maximum m_ref: the exponentials of step j are taken relative to the maximum of the steps BEFORE
+    // it (one step of lag; step 0 uses the maximum of its first 32 keys).  The row maximum of step j is collected
+    // in passing, off the critical path, and only moves m_ref for the next step (when it grew by more than 2^8);
+    // the matching rescale of O / the running sum happens at the next step, once P V (j) has landed.  Nothing has
+    // to be known about a step's scores before its first exponential, so S streams in 32-column chunks and the
+    // loads, the maxima and the MUFU work overlap.  bf16 P and the fp32 accumulators have the exponent range for
+    // any realistic growth inside one step; a row whose scores jump by more than 2^90 within a step (no finite
+    // softmax input does that in practice) is flagged and recomputed exactly by att_redo_kernel.
+    float m_ref = 0.f, l_run = 0.f, alpha_p = 1.f;
+    bool pend = false, any_pend = false, bad = false;
 
     for (int j = 0; j < n_kv; j++, g++) {
       mbar_wait(&bars->s_full[t], g & 1);
       tc_fence_after();
       const int valid = min(128, Nk - j * 128);  // columns of this tile that are real keys
-      uint32_t sv[128];
-      if (!(DBG & 2) || j == 0) {
-#pragma unroll
-        for (int ch = 0; ch < 4; ch++)
-          tmem_ld_32x32(lane_addr + COL_S + t * 128 + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[ch * 32]));
-        tmem_wait_ld();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->s_free[t]);   // S_t is in registers: the tensor pipe may overwrite it
-      if (valid < 128) {
-#pragma unroll
-        for (int i = 0; i < 128; i++)
-          if (i >= valid) sv[i] = 0xff800000u;  // -inf
-      }
-      // 8 independent chains of three-input maxima (a single long dependency chain is latency-bound with
-      // 2 warps per scheduler): 128 values in 64 FMNMX3
-      float mxa[8];
-#pragma unroll
-      for (int q = 0; q < 8; q++) mxa[q] = fmaxf(__uint_as_float(sv[q]), __uint_as_float(sv[8 + q]));
-      if (!(DBG & 16)) {
-#pragma unroll
-        for (int i = 16; i < 128; i += 16)
-#pragma unroll
-          for (int q = 0; q < 8; q++) mxa[q] = fmax3(mxa[q], __uint_as_float(sv[i + q]), __uint_as_float(sv[i + 8 + q]));
-      }
-      const float mx = fmaxf(fmax3(mxa[0], mxa[1], mxa[2]), fmax3(fmax3(mxa[3], mxa[4], mxa[5]), mxa[6], mxa[7]));
-      // lazy rescale decision (the O rescale itself is deferred until S has been consumed, so that
-      // the 128 S registers and the O staging registers are never live together)
-      float alpha = 1.f;
-      bool grow = false;
-      if (j == 0) {
-        m_used = mx;
-      } else {
-        grow = (mx - m_used) * c > 8.0f;
-        if (grow) {
-          alpha = fast_exp2((m_used - mx) * c);
-          m_used = mx;
-          l_run *= alpha;
-        }
-      }
-      const bool any_grow = __any_sync(0xffffffffu, grow);
-      const float mc = m_used * c;
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int half = 0; half < 2; half++) {   // two 64-key halves keep the packed-P registers short-lived
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          const int e = half * 64 + i;
-          auto ex = [](float x) { return (DBG & 1) ? fmaf(x, 0.5f, 1.0f) : fast_exp2(x); };
-          const float p0 = ex(fmaf(__uint_as_float(sv[e]), c, -mc));
-          const float p1 = ex(fmaf(__uint_as_float(sv[e + 1]), c, -mc));
-          const float p2 = ex(fmaf(__uint_as_float(sv[e + 2]), c, -mc));
-          const float p3 = ex(fmaf(__uint_as_float(sv[e + 3]), c, -mc));
-          if (!(DBG & 8)) { ls[0] += p0; ls[1] += p1; ls[2] += p2; ls[3] += p3; }
-          pk[i >> 1] = pack_bf16(p0, p1);
-          pk[(i >> 1) + 1] = pack_bf16(p2, p3);
-        }
-        if (half == 0 && j > 0) {
-          // P V (j-1) must have consumed P_t before it is overwritten (and O_t must be quiescent).  The wait sits
-          // AFTER the first 64 exponentials: they only need registers, so the previous step's P V (issue + 256
-          // tensor clocks + commit) completes behind ~512 MUFU clocks instead of stalling the group (the wait in
-          // front of the loop took 13.5 % of this kernel's stall samples, profiles/r2_attention_ncu.txt)
-          mbar_wait(&bars->o_full[t], (g - 1) & 1);
-          tc_fence_after();
-        }
-        if (!(DBG & 4)) tmem_st_32x32(lane_addr + COL_P + t * 64 + half * 32, pk);
-        else if (pk[(j + half) & 31] == 0x12345678u) l_run += 1.f;   // keep the values live
-      }
-      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      if (any_grow) {   // warp-uniform: rescale the running output of rows whose reference maximum moved
+      const bool waited = any_pend;
+      if (any_pend) {   // warp-uniform, rare: the reference maximum moved after the previous step -> rescale O now
+        mbar_wait(&bars->o_full[t], (g - 1) & 1);     // P V (j-1) has landed
+        tc_fence_after();
 #pragma unroll
         for (int ch = 0; ch < 2; ch++) {
           uint32_t r[32];
           tmem_ld_32x32(lane_addr + COL_O + t * 64 + ch * 32, r);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha_p);
           tmem_st_32x32(lane_addr + COL_O + t * 64 + ch * 32, r);
         }
+        tmem_wait_st();
       }
+      uint32_t sv[128];
+      tmem_ld_32x32(lane_addr + COL_S + t * 128, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+      tmem_wait_ld();
+#pragma unroll
+      for (int ch = 1; ch < 4; ch++)     // in flight while chunk 0 is exponentiated
+        tmem_ld_32x32(lane_addr + COL_S + t * 128 + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[ch * 32]));
+      if (valid < 128) {                 // ragged last K/V tile (warp-uniform, rare): mask the missing keys
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 128; i++)
+          if (i >= valid) sv[i] = 0xff800000u;  // -inf
+      }
+      // maximum of 32 scores: 4 chains of three-input maxima
+      auto max32 = [&](int base) {
+        float a0 = fmax3(__uint_as_float(sv[base]), __uint_as_float(sv[base + 1]), __uint_as_float(sv[base + 2]));
+        float a1 = fmax3(__uint_as_float(sv[base + 3]), __uint_as_float(sv[base + 4]), __uint_as_float(sv[base + 5]));
+        float a2 = fmax3(__uint_as_float(sv[base + 6]), __uint_as_float(sv[base + 7]), __uint_as_float(sv[base + 8]));
+        float a3 = fmax3(__uint_as_float(sv[base + 9]), __uint_as_float(sv[base + 10]), __uint_as_float(sv[base + 11]));
+#pragma unroll
+        for (int i = 12; i < 28; i += 8) {
+          a0 = fmax3(a0, __uint_as_float(sv[base + i]), __uint_as_float(sv[base + i + 1]));
+          a1 = fmax3(a1, __uint_as_float(sv[base + i + 2]), __uint_as_float(sv[base + i + 3]));
+          a2 = fmax3(a2, __uint_as_float(sv[base + i + 4]), __uint_as_float(sv[base + i + 5]));
+          a3 = fmax3(a3, __uint_as_float(sv[base + i + 6]), __uint_as_float(sv[base + i + 7]));
+        }
+        a0 = fmax3(a0, __uint_as_float(sv[base + 28]), __uint_as_float(sv[base + 29]));
+        a1 = fmax3(a1, __uint_as_float(sv[base + 30]), __uint_as_float(sv[base + 31]));
+        return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+      };
+      float mx = max32(0);
+      if (j == 0) m_ref = mx;
+      const float mc = m_ref * c;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[32];
+      // 32 exponentials of chunk `ch` -> 16 packed bf16 pairs at pk[(ch & 1) * 16 ...]
+      auto exp32 = [&](int ch) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const int e = ch * 32 + i;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), c, -mc));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), c, -mc));
+          const float p2 = fast_exp2(fmaf(__uint_as_float(sv[e + 2]), c, -mc));
+          const float p3 = fast_exp2(fmaf(__uint_as_float(sv[e + 3]), c, -mc));
+          ls[0] += p0; ls[1] += p1; ls[2] += p2; ls[3] += p3;
+          pk[(ch & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
+          pk[(ch & 1) * 16 + (i >> 1) + 1] = pack_bf16(p2, p3);
+        }
+      };
+      exp32(0);
+      tmem_wait_ld();                  // chunks 1-3 have landed behind the first 32 exponentials
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->s_free[t]);   // S_t is in registers: the tensor pipe may overwrite it
+      exp32(1);
+      mx = fmax3(mx, max32(32), max32(64));
+      mx = fmaxf(mx, max32(96));
+      if (j > 0 && !waited) {
+        // P V (j-1) must have consumed P_t before it is overwritten; by now that MMA (issue + 256 tensor clocks +
+        // commit) has had 64 exponentials of time
+        mbar_wait(&bars->o_full[t], (g - 1) & 1);
+        tc_fence_after();
+      }
+      tmem_st_32x32(lane_addr + COL_P + t * 64, pk);
+      exp32(2);
+      exp32(3);
+      tmem_st_32x32(lane_addr + COL_P + t * 64 + 32, pk);
+      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      // the reference for the NEXT step (not after the last one: the final division wants O and the sum in one frame)
+      const float growth = (mx - m_ref) * c;
+      bad = bad || growth > 90.f;
+      pend = (j + 1 < n_kv) && growth > 8.0f;
+      alpha_p = 1.f;
+      if (pend) {
+        alpha_p = fast_exp2(-growth);
+        m_ref = mx;
+        l_run *= alpha_p;
+      }
+      any_pend = __any_sync(0xffffffffu, pend);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -316,6 +342,12 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
                              pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv),
                              pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv),
                              pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv));
+        if (bad && p.redo != nullptr) {   // (practically never) hand the row to the exact recomputation
+          const int slot = atomicAdd(p.redo, 1);
+          if (slot < p.redo_cap)
+            reinterpret_cast<int4*>(p.redo + 4)[slot] =
+                make_int4((int)(w.qrow + t * 128 + row_in_tile), w.head, (int)w.krow, Nk);
+        }
       }
     }
     }  // units
@@ -325,16 +357,53 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
   if (warp == 1) tmem_dealloc<NT * 256>(tmem);
 }
 
-template <int NT, int DBG = 0>
+// Exact recomputation of the rows the main kernel flagged (a score jump of more than 2^90 inside one K/V step; see
+// the softmax warpgroups): plain online softmax in fp32, one warp per (query row, head), lane = two head dims.
+// One block; with an empty list -- the normal case -- it returns at once.  Leaves the list empty.
+__global__ void __launch_bounds__(256) att_redo_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                       __nv_bfloat16* __restrict__ out, int* __restrict__ redo, int cap) {
+  const int n = min(redo[0], cap);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float c = 0.125f * 1.4426950408889634f;
+  for (int e = warp; e < n; e += 8) {
+    const int4 ent = reinterpret_cast<const int4*>(redo + 4)[e];
+    const long long qrow = ent.x, krow = ent.z;
+    const int head = ent.y, Nk = ent.w;
+    const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(qkv + qrow * 768 + head * 64 + 2 * lane);
+    const float qx = __bfloat162float(q2.x), qy = __bfloat162float(q2.y);
+    float m = -INFINITY, l = 0.f, ox = 0.f, oy = 0.f;
+    for (int j = 0; j < Nk; j++) {
+      const __nv_bfloat16* kr = qkv + (krow + j) * 768 + 256 + head * 64 + 2 * lane;
+      const __nv_bfloat162 k2 = *reinterpret_cast<const __nv_bfloat162*>(kr);
+      const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(kr + 256);
+      const float s = warp_sum(qx * __bfloat162float(k2.x) + qy * __bfloat162float(k2.y)) * c;
+      const float mn = fmaxf(m, s);
+      const float scale = exp2f(m - mn), pj = exp2f(s - mn);
+      l = l * scale + pj;
+      ox = ox * scale + pj * __bfloat162float(v2.x);
+      oy = oy * scale + pj * __bfloat162float(v2.y);
+      m = mn;
+    }
+    *reinterpret_cast<__nv_bfloat162*>(out + qrow * 256 + head * 64 + 2 * lane) = __floats2bfloat162_rn(ox / l, oy / l);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) redo[0] = 0;
+}
+
+template <int NT>
 int launch_att(const TcAttn& p, const CUtensorMap& map, int num_sms, cudaStream_t st) {
   const int qt0 = cdiv(p.Nq[0], NT * 128), qt1 = p.Nq[1] > 0 ? cdiv(p.Nq[1], NT * 128) : 0;
   const int units0 = p.B * 4 * qt0, units1 = p.B * 4 * qt1;
   const int n_units = units0 + units1;
   const size_t smem = (size_t)(2 * NT + 2 * KV_STAGES) * TILE_BYTES + sizeof(AttBars) + 1024;
-  SFM_SMEM_OPT_IN((tc_attention_kernel<NT, DBG>), smem);
+  SFM_SMEM_OPT_IN(tc_attention_kernel<NT>, smem);
   const int grid = std::min(n_units, num_sms);
-  tc_attention_kernel<NT, DBG><<<grid, AttCfg<NT>::THREADS, smem, st>>>(map, p, units0, qt0, qt1 > 0 ? qt1 : 1, n_units);
+  tc_attention_kernel<NT><<<grid, AttCfg<NT>::THREADS, smem, st>>>(map, p, units0, qt0, qt1 > 0 ? qt1 : 1, n_units);
   SFM_LAUNCH_CHECK();
+  if (p.redo != nullptr) {
+    att_redo_kernel<<<1, 256, 0, st>>>(p.qkv, p.out, p.redo, p.redo_cap);
+    SFM_LAUNCH_CHECK();
+  }
   return SFM_OK;
 }
 
@@ -350,18 +419,6 @@ int tc_attention(const TcAttn& p, int num_sms, cudaStream_t st) {
   TcAttn q = p;
   q.stagger = stagger;
   SFM_REQUIRE(num_sms > 0, "tc_attention: bad SM count");
-#ifdef SFM_ATT_EXPERIMENTS
-  switch (getenv("SFM_ATT_DBG") ? atoi(getenv("SFM_ATT_DBG")) : 0) {
-    case 1: return launch_att<2, 1>(q, map, num_sms, st);
-    case 2: return launch_att<2, 2>(q, map, num_sms, st);
-    case 4: return launch_att<2, 4>(q, map, num_sms, st);
-    case 8: return launch_att<2, 8>(q, map, num_sms, st);
-    case 16: return launch_att<2, 16>(q, map, num_sms, st);
-    case 9: return launch_att<2, 9>(q, map, num_sms, st);
-    case 31: return launch_att<2, 31>(q, map, num_sms, st);
-    default: break;
-  }
-#endif
   if (nt == 1) return launch_att<1>(q, map, num_sms, st);
   return launch_att<2>(q, map, num_sms, st);
 }

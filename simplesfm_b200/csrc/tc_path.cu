@@ -100,6 +100,7 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
       ProfScope ps(h, SFM_PROF_ATTENTION, st);
       TcAttn a;
       a.tmaps = h->tmaps;
+      a.redo = h->att_redo; a.redo_cap = ATT_REDO_CAP;
       a.qkv = b.qkv; a.rows_total = T; a.out = b.msgp; a.B = c.B;
       a.Nq[0] = c.K0; a.Nq[1] = c.K1;
       a.q_row0[0] = 0; a.q_row0[1] = T0;

@@ -78,7 +78,12 @@ struct TcAttn {
   long long q_row0[2] = {0, 0}, k_row0[2] = {0, 0};
   int stagger = 1;   // tile 1 of a CTA runs half a K/V step behind tile 0 (ping-pong on the MUFU pipe)
   TmapCache* tmaps = nullptr;   // the handle's tensor-map cache (optional)
+  // exact-recomputation list (handle-owned, zero on entry, left zero): redo[0] = count, entries int4 from redo + 4
+  int* redo = nullptr;
+  int redo_cap = 0;
 };
+constexpr int ATT_REDO_CAP = 4096;
+inline size_t att_redo_bytes() { return (size_t)(4 + 4 * ATT_REDO_CAP) * sizeof(int); }
 int tc_attention(const TcAttn& p, int num_sms, cudaStream_t st);
 
 // 3x3 / pad 1 convolution, NHWC bf16, implicit GEMM on tcgen05 with 4-D TMA im2col (tc_conv.cu)
