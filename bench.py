@@ -287,7 +287,10 @@ def run_ours(a):
     e2e_images = None
     if not a.no_images:
         own = [i for i in range(n_img) if i % world == rank]
-        pix = {i: (synthetic.textured_image(1000 + i)[0, 0] * 255).round().to(torch.uint8).numpy() for i in own}
+        # overlapping views of ONE textured scene (windows of the same texture, shifted), so that the matches are real
+        # correspondences and the detector-precision comparison below means something
+        pix = {i: (synthetic.textured_image(1000, shift=(7 * (i % 15) - 49, 11 * ((i * 7) % 11) - 55))[0, 0] * 255)
+               .round().to(torch.uint8).numpy() for i in own}
         items = [(pix.get(i), None) for i in range(n_img)]          # a rank only touches the images it extracts
 
         def step_images():
@@ -304,7 +307,51 @@ def run_ours(a):
                                   "SuperGlue on this rank's pairs, table gather to rank 0, D2H"}
         if rank == 0:
             e2e_images["matches_per_step"] = int(sum(len(v) for v in table_img.values()))
-        del frames_img, table_img
+        # the same pipeline with the tcgen05 (bf16) SuperPoint: stated precision, a slightly different detector --
+        # its end-to-end agreement with the exact-SuperPoint tables is measured here through keypoint coordinates
+        other = "bf16" if a.sp_precision == "fp32" else "fp32"
+        m_alt = make_matcher(sp_precision=other)
+
+        def step_images_alt():
+            frames = m_alt._frames_from(iter(items))
+            return frames, m_alt.match_frames(frames, names, None)[1]
+
+        step_images_alt()
+        n_alt = max(1, min(a.steps, 3))
+        ms_alt, (frames_alt, table_alt) = timed(step_images_alt, n_alt)
+        alt = {"value": n_pairs * n_alt / (ms_alt / 1e3), "unit": "pairs/s", "ms_per_step": ms_alt / n_alt,
+               "superpoint_precision": other}
+        if rank == 0:
+            kp_a = [f.keypoints_poses.cpu().numpy() for f in frames_img]
+            kp_b = [f.keypoints_poses.cpu().numpy() for f in frames_alt]
+            same_kp = sum(len({tuple(x) for x in ka.tolist()} & {tuple(x) for x in kb.tolist()}) for ka, kb in zip(kp_a, kp_b))
+            inter = union = 0
+            for k in list(table_img.keys())[:100]:
+                i, j = int(k[0]) - 1, int(k[1]) - 1
+                sa = {(tuple(kp_a[i][r[0]]), tuple(kp_a[j][r[1]])) for r in table_img[k].tolist()}
+                sb = {(tuple(kp_b[i][r[0]]), tuple(kp_b[j][r[1]])) for r in table_alt[k].tolist()}
+                inter += len(sa & sb)
+                union += len(sa | sb)
+            # descriptors of the keypoints both detectors found (first 8 images): cosine similarity
+            cos = []
+            for fa, fb, ka, kb in list(zip(frames_img, frames_alt, kp_a, kp_b))[:8]:
+                ib = {tuple(x): j for j, x in enumerate(kb.tolist())}
+                pairs_ab = [(i, ib[tuple(x)]) for i, x in enumerate(ka.tolist()) if tuple(x) in ib]
+                if pairs_ab:
+                    ia = torch.tensor([p[0] for p in pairs_ab], device=dev)
+                    jb = torch.tensor([p[1] for p in pairs_ab], device=dev)
+                    cos.append((fa.descriptors[:, ia] * fb.descriptors[:, jb]).sum(0))
+            if cos:
+                cos = torch.cat(cos)
+                alt["descriptor_cosine_mean_min_on_common_keypoints"] = [float(cos.mean()), float(cos.min())]
+            alt["note"] = ("random synthetic SuperPoint weights give few, near-threshold matches per image pair "
+                           "(matches_per_step), so the table agreement of two detectors is dominated by threshold "
+                           "flips; keypoint overlap and descriptor cosine are the informative figures")
+            alt["keypoint_overlap_with_" + a.sp_precision] = same_kp / max(sum(len(k) for k in kp_a), 1)
+            alt["match_table_agreement_with_" + a.sp_precision] = inter / max(union, 1)
+            alt["agreement_pairs"] = min(100, len(table_img))
+        e2e_images["alternative_superpoint"] = alt
+        del frames_img, table_img, frames_alt, table_alt, m_alt
 
     # ---- determinism across rank counts: the 50-image scene matched with THIS world size
     sub_n = min(50, n_img)
@@ -355,6 +402,11 @@ def run_ours(a):
                 "traffic_source": traffic_src,
                 "peak_source": peak_src, "flop_per_launch": flop_group, "ms_per_launch": att_total_ms / att_groups,
                 "launches": att_groups, "rank": rank,
+                # the kernel's own bound at head dim 64: one ex2 per 256 tensor FLOPs, 16 ex2 / clk / SM on the MUFU
+                # pipe (tools/micro/exp_mix_bench.cu) -> 148 SMs x 16 x clock x 256 FLOP
+                "mufu_bound": (lambda mhz: None if not mhz else {
+                    "peak_tflops_at_run_clock": 148 * 16 * mhz * 1e6 * 256 / 1e12, "sm_mhz": mhz,
+                    "frac": achieved / (148 * 16 * mhz * 1e6 * 256 / 1e12)})(clocks.get("sm_mhz")),
                 "share_of_step": {k: float(prof_ms[i]) / ms for i, k in
                                   enumerate(["linear", "attention", "sinkhorn_match", "other"])}}
 

@@ -133,6 +133,25 @@ SFM_API int sfm_superglue_forward(sfm_handle_t h,
                           int chunk_groups,
                           int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* Layer-0 hoisting for eval-mode BatchNorm (bf16 path).  GNN layer 0 is a SELF layer (superglue.py:131-139 with
+ * names[0] == 'self'), so `desc + kenc(kpts, scores)` (superglue.py:254-255) and the layer-0 update depend on one image
+ * alone when BatchNorm uses running statistics: they are computed ONCE PER IMAGE here instead of once per pair.
+ *   hoist_layer0   : records of n_img images (K keypoints each, same layout as sfm_superglue_forward's inputs)
+ *                    -> x_store [n_img, K, 256] f32, the residual stream entering layer 1.
+ *                    Workspace: sfm_superglue_workspace_bytes(n_img, K, K, precision, 1) is sufficient.
+ *   forward_hoisted: the rest of SuperGlue.forward (layers 1..17, final projection, optimal transport, mutual
+ *                    matches) for B pairs gathered from the stores by idx0 / idx1 (int32 [B], NULL = identity).
+ *                    Results are bit-identical to sfm_superglue_forward with bn_mode = eval on the same keypoints
+ *                    (tests/test_gpu_hoist.py). */
+SFM_API int sfm_superglue_hoist_layer0(sfm_handle_t h, const float* desc, const float* kpts, const float* scores,
+                                       int ldk, int kcap, int n_img, int K, int H, int W, int precision,
+                                       float* x_store, void* workspace, size_t workspace_bytes, void* stream);
+SFM_API int sfm_superglue_forward_hoisted(sfm_handle_t h, const float* x_store0, int store_k0, const int* idx0,
+                                          const float* x_store1, int store_k1, const int* idx1, int B, int K0, int K1,
+                                          int sinkhorn_iterations, float match_threshold, int precision,
+                                          int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
+                                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* parity taps into the forward workspace: which = 0 descriptors after kenc (token-major
  * [B*K0 + B*K1, 256]), 1 after the GNN, 2 score matrix [B,K0,K1], 3 u [B,K0+1], 4 v [B,K1+1] */
 SFM_API int sfm_superglue_tap(int B, int K0, int K1, int precision, int chunk_groups, int which, void* workspace,

@@ -384,6 +384,7 @@ static SgCall shape_call(int B, int K0, int K1, int precision, int groups) {
   SgCall c;
   memset(&c, 0, sizeof(c));
   c.B = B; c.K0 = K0; c.K1 = K1; c.precision = precision; c.groups = groups;
+  c.last_layer = 18;
   return c;
 }
 
@@ -411,6 +412,40 @@ int sfm_superglue_forward(sfm_handle_t h, const float* desc0, const float* kpts0
   c.B = B; c.K0 = K0; c.K1 = K1; c.H0 = H0; c.W0 = W0; c.H1 = H1; c.W1 = W1;
   c.iters = sinkhorn_iterations; c.thr = match_threshold; c.bn_mode = bn_mode; c.precision = precision;
   c.groups = chunk_groups;
+  c.m0 = (long long*)matches0; c.m1 = (long long*)matches1; c.ms0 = mscores0; c.ms1 = mscores1;
+  return sg_forward(h, c, ws, ws_bytes, false, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int sfm_superglue_hoist_layer0(sfm_handle_t h, const float* desc, const float* kpts, const float* scores, int ldk,
+                               int kcap, int n_img, int K, int H, int W, int precision, float* x_store, void* ws,
+                               size_t ws_bytes, void* stream) {
+  SFM_REQUIRE(h, "sfm_superglue_hoist_layer0: NULL handle");
+  SFM_REQUIRE(n_img == 0 || (desc && kpts && scores && x_store), "sfm_superglue_hoist_layer0: NULL argument");
+  SFM_REQUIRE(K > 0 && K <= ldk && K <= kcap, "sfm_superglue_hoist_layer0: K exceeds record size");
+  SgCall c = shape_call(n_img, K, 0, precision, 1);
+  c.desc0 = desc; c.kpts0 = kpts; c.scores0 = scores; c.ldk0 = ldk; c.kcap0 = kcap;
+  c.H0 = H; c.W0 = W; c.H1 = H; c.W1 = W;
+  c.bn_mode = 1;            // running statistics: the only mode in which layer 0 is independent of the pair
+  c.last_layer = 1;
+  c.x_out = x_store;
+  return sg_forward(h, c, ws, ws_bytes, false, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int sfm_superglue_forward_hoisted(sfm_handle_t h, const float* x_store0, int store_k0, const int* idx0,
+                                  const float* x_store1, int store_k1, const int* idx1, int B, int K0, int K1,
+                                  int sinkhorn_iterations, float match_threshold, int precision, int64_t* matches0,
+                                  int64_t* matches1, float* mscores0, float* mscores1, void* ws, size_t ws_bytes,
+                                  void* stream) {
+  SFM_REQUIRE(h, "sfm_superglue_forward_hoisted: NULL handle");
+  SFM_REQUIRE(B == 0 || (x_store0 && x_store1), "sfm_superglue_forward_hoisted: NULL input");
+  SFM_REQUIRE(B == 0 || (matches0 && matches1 && mscores0 && mscores1), "sfm_superglue_forward_hoisted: NULL output");
+  SFM_REQUIRE(sinkhorn_iterations >= 0, "sfm_superglue_forward_hoisted: negative sinkhorn_iterations");
+  SgCall c = shape_call(B, K0, K1, precision, 1);
+  c.xs0 = x_store0; c.xs_k0 = store_k0; c.idx0 = idx0;
+  c.xs1 = x_store1; c.xs_k1 = store_k1; c.idx1 = idx1;
+  c.first_layer = 1;
+  c.bn_mode = 1;
+  c.iters = sinkhorn_iterations; c.thr = match_threshold;
   c.m0 = (long long*)matches0; c.m1 = (long long*)matches1; c.ms0 = mscores0; c.ms1 = mscores1;
   return sg_forward(h, c, ws, ws_bytes, false, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
 }

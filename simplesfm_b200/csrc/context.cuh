@@ -107,6 +107,15 @@ struct SgCall {
   int groups;  // number of BatchNorm statistic groups (fused Matcher chunks); B % groups == 0
   long long *m0, *m1;
   float *ms0, *ms1;
+  // Layer-0 hoisting (eval-mode BatchNorm only): GNN layer 0 is a SELF layer, so desc + kenc and the
+  // layer-0 update depend on one image alone and can be computed once per image instead of once per pair.
+  //   last_layer < 18 : stop after GNN layer `last_layer - 1` and copy the residual stream to x_out (K1 may be 0)
+  //   xs0 / xs1 != 0  : per-image stores [n_img, xs_k, 256] f32 of the residual stream entering layer `first_layer`;
+  //                     the pair batch is gathered from them (idx0 / idx1) instead of running the front end
+  int first_layer = 0, last_layer = 18;
+  const float *xs0 = nullptr, *xs1 = nullptr;
+  int xs_k0 = 0, xs_k1 = 0;
+  float* x_out = nullptr;
 };
 // dry = true: only compute the workspace size / tap offsets (no launches, h may be null)
 int sg_forward(sfm_ctx* h, const SgCall& c, void* ws, size_t ws_bytes, bool dry, size_t* need, int tap_which,

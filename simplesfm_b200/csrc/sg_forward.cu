@@ -50,7 +50,8 @@ int carve(Arena& a, const SgCall& c, SgBuffers& b) {
   b.scores = a.get<float>((size_t)c.B * c.K0 * c.K1);
   b.u = a.get<float>((size_t)c.B * (c.K0 + 1));
   b.v = a.get<float>((size_t)c.B * (c.K1 + 1));
-  b.part = a.get<float>(sinkhorn_partial_floats(c.B, c.K0, c.K1, &b.R));
+  b.R = 1;
+  b.part = c.K1 > 0 ? a.get<float>(sinkhorn_partial_floats(c.B, c.K0, c.K1, &b.R)) : nullptr;   // (K1 == 0: hoisting pass)
   b.counters = a.get<int>(sinkhorn_counter_ints(c.B, c.K1));
   b.sk_fused = c.precision == 1 ? a.get<float>(sinkhorn_fused_floats(c.B, c.K0, c.K1)) : nullptr;
   b.sk_kb = c.precision == 1 ? a.get<float>((size_t)c.B * c.K0) : nullptr;
@@ -187,8 +188,14 @@ int forward_f32(sfm_ctx* h, const SgCall& c, const SgBuffers& b, cudaStream_t st
 
 int sg_forward(sfm_ctx* h, const SgCall& c, void* ws, size_t ws_bytes, bool dry, size_t* need, int tap_which,
                float** tap_ptr, size_t* tap_floats, cudaStream_t st) {
-  SFM_REQUIRE(c.B >= 0 && c.K0 > 0 && c.K1 > 0, "superglue: B >= 0 and K0, K1 > 0 required (B=%d K0=%d K1=%d)", c.B,
-              c.K0, c.K1);
+  const bool hoist_pass = c.last_layer < 18;
+  SFM_REQUIRE(c.B >= 0 && c.K0 > 0 && (c.K1 > 0 || (hoist_pass && c.K1 == 0)),
+              "superglue: B >= 0 and K0, K1 > 0 required (B=%d K0=%d K1=%d)", c.B, c.K0, c.K1);
+  SFM_REQUIRE((c.first_layer == 0 && c.last_layer == 18) || (c.precision == 1 && c.bn_mode == 1),
+              "superglue: layer-0 hoisting exists for the bf16 path with eval-mode BatchNorm only");
+  SFM_REQUIRE(c.first_layer >= 0 && c.first_layer <= 1 && c.last_layer >= 1 && c.last_layer <= 18 &&
+                  (c.first_layer == 0 || (c.xs0 && c.xs1 && c.xs_k0 >= c.K0 && c.xs_k1 >= c.K1)) &&
+                  (!hoist_pass || c.x_out), "superglue: bad hoisting arguments");
   SFM_REQUIRE(c.precision == 0 || c.precision == 1, "superglue: unknown precision %d", c.precision);
   SFM_REQUIRE(c.bn_mode == 0 || c.bn_mode == 1, "superglue: unknown bn_mode %d", c.bn_mode);
   SFM_REQUIRE(c.groups >= 0 && (c.groups <= 1 || c.B % c.groups == 0), "superglue: B=%d is not divisible into %d chunk groups", c.B, c.groups);
@@ -226,16 +233,25 @@ int sg_forward(sfm_ctx* h, const SgCall& c, void* ws, size_t ws_bytes, bool dry,
   SFM_REQUIRE(h != nullptr && h->sg.loaded, "superglue: weights not loaded (call sfm_load_superglue)");
   if (c.B == 0) return SFM_OK;
   const long long T0 = (long long)c.B * c.K0;
-  SFM_CUDA(cudaMemsetAsync(b.counters, 0, sinkhorn_counter_ints(c.B, c.K1) * sizeof(int), st));
-  SFM_TRY(sg_frontend(c.desc0, 256ll * c.ldk0, c.ldk0, c.kpts0, c.scores0, c.kcap0, c.idx0, c.B, c.K0, c.H0, c.W0,
-                      b.X, b.kin, st));
-  SFM_TRY(sg_frontend(c.desc1, 256ll * c.ldk1, c.ldk1, c.kpts1, c.scores1, c.kcap1, c.idx1, c.B, c.K1, c.H1, c.W1,
-                      b.X + T0 * 256, b.kin + T0 * 4, st));
+  if (c.K1 > 0) SFM_CUDA(cudaMemsetAsync(b.counters, 0, sinkhorn_counter_ints(c.B, c.K1) * sizeof(int), st));
+  if (c.first_layer > 0) {
+    SFM_TRY(gather_tokens(c.xs0, c.xs_k0, c.idx0, c.B, c.K0, b.X, st));
+    SFM_TRY(gather_tokens(c.xs1, c.xs_k1, c.idx1, c.B, c.K1, b.X + T0 * 256, st));
+  } else {
+    SFM_TRY(sg_frontend(c.desc0, 256ll * c.ldk0, c.ldk0, c.kpts0, c.scores0, c.kcap0, c.idx0, c.B, c.K0, c.H0, c.W0,
+                        b.X, b.kin, st));
+    SFM_TRY(sg_frontend(c.desc1, 256ll * c.ldk1, c.ldk1, c.kpts1, c.scores1, c.kcap1, c.idx1, c.B, c.K1, c.H1, c.W1,
+                        b.X + T0 * 256, b.kin + T0 * 4, st));
+  }
   if (c.precision == 0) {
     SFM_TRY(forward_f32(h, c, b, st));
   } else {
     tb.t0 = b.t0; tb.t1 = b.t1; tb.bn_part = b.bn_part; tb.bn_scale = b.bn_scale; tb.bn_shift = b.bn_shift;
     SFM_TRY(tc_sg_forward(h, c, b.X, b.kin, b.scores, tb, st));
+  }
+  if (hoist_pass) {   // the residual stream after layer `last_layer - 1`, token-major, one block per image
+    SFM_CUDA(cudaMemcpyAsync(c.x_out, b.X, sizeof(float) * 256 * (size_t)c.B * (c.K0 + c.K1), cudaMemcpyDeviceToDevice, st));
+    return SFM_OK;
   }
   SinkhornArgs s;
   s.S = b.scores; s.B = c.B; s.N = c.K0; s.M = c.K1; s.alpha = h->sg.bin_score; s.iters = c.iters;

@@ -775,6 +775,22 @@ __global__ void __launch_bounds__(256) compact_kernel(const long long* __restric
   if (threadIdx.x == 0) lengths[b] = running;
 }
 
+// X[b * K + k, :] = store[idx[b] * store_k + k, :]   (256 floats per row; one warp per row, float4 x 2 per lane)
+__global__ void __launch_bounds__(256) gather_tokens_kernel(const float4* __restrict__ store, int store_k,
+                                                            const int* __restrict__ idx, int K,
+                                                            float4* __restrict__ X, long long rows) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const long long b = row / K;
+  const int k = (int)(row - b * K);
+  const long long img = idx ? idx[b] : b;
+  const float4* src = store + (img * store_k + k) * 64;
+  float4* dst = X + row * 64;
+  dst[lane] = src[lane];
+  dst[lane + 32] = src[lane + 32];
+}
+
 // rows [0, lengths[p]) of every pair's (kcap, 2) table -> one flat (sum lengths, 2) array at offsets[p]
 __global__ void __launch_bounds__(256) pack_tables_kernel(const uint2* __restrict__ tables, int kcap,
                                                           const int* __restrict__ lengths,
@@ -1071,6 +1087,15 @@ int sinkhorn_write_Z(const SinkhornArgs& a, float* Z, cudaStream_t st) {
   const float norm = -logf((float)a.N + (float)a.M);
   dim3 grid(cdiv(a.M + 1, 256), a.N + 1, a.B);
   write_Z_kernel<<<grid, 256, 0, st>>>(a.S, a.N, a.M, a.alpha, a.u, a.v, norm, Z);
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+int gather_tokens(const float* store, int store_k, const int* idx, int B, int K, float* X, cudaStream_t st) {
+  const long long rows = (long long)B * K;
+  if (rows == 0) return SFM_OK;
+  gather_tokens_kernel<<<cdiv(rows, 8), 256, 0, st>>>(reinterpret_cast<const float4*>(store), store_k, idx, K,
+                                                      reinterpret_cast<float4*>(X), rows);
   SFM_LAUNCH_CHECK();
   return SFM_OK;
 }

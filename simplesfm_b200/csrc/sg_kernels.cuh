@@ -15,6 +15,9 @@ int sg_frontend(const float* desc, long long desc_img_stride, int ldk, const flo
                 int kcap, const int* idx, int B, int K, int imgH, int imgW, float* X, float* kin,
                 cudaStream_t st);
 
+// pair batch gathered from a per-image token-major store [n_img, store_k, 256] (layer-0 hoisting)
+int gather_tokens(const float* store, int store_k, const int* idx, int B, int K, float* X, cudaStream_t st);
+
 // in-place softmax over the last dim of [rows, M] (ld)
 int softmax_rows_f32(float* S, long long rows, int M, int ld, cudaStream_t st);
 // batched 2-D transpose, batch index z -> offsets bs?0 * (z / nb1) + bs?1 * (z % nb1)

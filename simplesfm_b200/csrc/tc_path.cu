@@ -39,7 +39,12 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
     g.out_f = out_f; g.out_f_ld = 256; g.accumulate_f = accumulate;
     return tc_gemm(g, sms, st);
   };
-  {
+  if (c.first_layer > 0) {
+    // the residual stream entering layer `first_layer` was gathered from the per-image stores: only its bf16 shadow
+    // is missing
+    ProfScope ps(h, SFM_PROF_OTHER, st);
+    SFM_TRY(f32_to_bf16(X, b.xh, T * 256, st));
+  } else {
     // ---- keypoint encoder (superglue.py:72-82): 3->32->64->128 on the fp32 FFMA GEMM (keypoint coordinates
     // stay fp32), the two wide layers 128->256->256 on tcgen05; the last layer accumulates straight into the
     // fp32 residual stream X and emits its bf16 shadow.
@@ -92,7 +97,7 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
   static const bool no_bn_fusion = getenv("SFM_NO_BN_FUSION") != nullptr;   // read once per process (A/B knob)
   const bool fuse_bn = train && T0 % gr.G == 0 && T1 % gr.G == 0 && (T0 / gr.G) % 128 == 0 && (T1 / gr.G) % 128 == 0 &&
                        T0 > 0 && T1 > 0 && !no_bn_fusion;
-  for (int l = 0; l < 18; l++) {
+  for (int l = c.first_layer; l < c.last_layer; l++) {
     const SgLayer& L = w.L[l];
     const bool cross = l & 1;
     SFM_TRY(linear(b.xh, 256, nullptr, 0, 256, 256, L.Wqkv_h, 768, L.bqkv, 0, b.qkv, 768, nullptr, 0));
@@ -153,6 +158,7 @@ int tc_sg_forward(sfm_ctx* h, const SgCall& c, float* X, const float* kin, float
     }
     SFM_TRY(linear(b.hid, 512, nullptr, 0, 512, 512, L.W2_h, 256, L.b2, 0, b.xh, 256, X, 1));
   }
+  if (c.last_layer < 18) return SFM_OK;   // hoisting pass: the caller takes X
   SFM_TRY(linear(b.xh, 256, nullptr, 0, 256, 256, w.Wf_h, 256, w.bf, 0, b.mdh, 256, nullptr, 0));
   // scores_b = md0_b md1_b^T / 16  (superglue.py:264-265): batched, "weights" = the pair's side-1 descriptors
   ProfScope ps(h, SFM_PROF_LINEAR, st);

@@ -96,7 +96,8 @@ class Matcher(object):
                  extract_batch: int = 8,
                  decode_threads: int = 4,
                  process_group=None,
-                 gather_tables: str = 'root'):
+                 gather_tables: str = 'root',
+                 hoist_layer0: bool = True):
 
         self.matcher_type = matcher_type
         self.device = torch.device(device)
@@ -108,6 +109,9 @@ class Matcher(object):
         if gather_tables not in ('root', 'none'):
             raise ValueError("gather_tables must be 'root' or 'none'")
         self.gather_tables = gather_tables
+        # eval-mode BatchNorm + bf16 path only: GNN layer 0 (a self layer) once per image instead of once per pair
+        # (SURVEY.md H9); bit-identical results, used when no chunk truncates its keypoints
+        self.hoist_layer0 = bool(hoist_layer0)
         # consecutive chunks with identical keypoint counts are launched together (better GPU occupancy);
         # BatchNorm statistics stay per chunk, so results equal the chunk-by-chunk loop of the reference
         self.fuse_chunks = max(1, int(fuse_chunks)) if precision == 'bf16' else 1
@@ -169,6 +173,23 @@ class Matcher(object):
         # chunks per launch: bounded so that one launch holds at most 256 pairs (score matrices + activations of a
         # launch at 4096 keypoints stay around 35 GB)
         fuse_limit = max(1, min(self.fuse_chunks, 256 // bs))
+        # layer-0 hoisting: valid when BatchNorm uses running statistics and no chunk truncates (equal counts)
+        xstore = None
+        if (self.hoist_layer0 and sg.can_hoist() and uniform_hw and len(counts) and counts.min() == counts.max()
+                and counts[0] > 0):
+            used = np.unique(pairs0)
+            K = int(counts[0])
+            xstore = torch.empty(len(counts), K, 256, dtype=torch.float32, device=dev)
+            for i0 in range(0, len(used), 64):      # 64 images per pass bounds the workspace
+                blk = used[i0:i0 + 64]
+                if len(blk) == blk[-1] - blk[0] + 1:     # contiguous run of image indices: no gather needed
+                    lo, hi = int(blk[0]), int(blk[-1]) + 1
+                    xstore[lo:hi] = sg.hoist_layer0(store.desc[lo:hi], store.kpts[lo:hi], store.scores[lo:hi],
+                                                    hi - lo, K, store.hw[0])
+                else:
+                    sel = torch.from_numpy(blk.astype(np.int64)).to(dev)
+                    xstore[sel] = sg.hoist_layer0(store.desc[sel].contiguous(), store.kpts[sel].contiguous(),
+                                                  store.scores[sel].contiguous(), len(blk), K, store.hw[0])
         parts = []
         for s0 in range(0, P, super_chunk):
             s1 = min(P, s0 + super_chunk)
@@ -210,9 +231,12 @@ class Matcher(object):
                 c1 = c0 + B
                 if k0 == 0 or k1 == 0:      # reference early-out: no matches (superglue.py:240-247)
                     continue
-                m0, _, _, _, _ = sg.match_records(store.desc, store.kpts, store.scores, idx0_all[c0:c1],
-                                                  store.desc, store.kpts, store.scores, idx1_all[c0:c1],
-                                                  B, k0, k1, hw0, hw1, chunk_groups=groups)
+                if xstore is not None:
+                    m0, _, _, _, _ = sg.match_hoisted(xstore, idx0_all[c0:c1], xstore, idx1_all[c0:c1], B, k0, k1)
+                else:
+                    m0, _, _, _, _ = sg.match_records(store.desc, store.kpts, store.scores, idx0_all[c0:c1],
+                                                      store.desc, store.kpts, store.scores, idx1_all[c0:c1],
+                                                      B, k0, k1, hw0, hw1, chunk_groups=groups)
                 # compact into the super-chunk table; rows of pair p start at tables[p - s0]
                 tview = tables[c0 - s0:c1 - s0]
                 if k0 == store.kcap:

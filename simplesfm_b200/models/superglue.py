@@ -163,6 +163,42 @@ class SuperGlue:
                 ptr(m0), ptr(m1), ptr(s0), ptr(s1), ptr(ws), ws.numel(), stream_ptr(dev)))
         return m0, m1, s0, s1, ws
 
+    # ---- layer-0 hoisting (eval-mode BatchNorm, bf16 path) --------------------------------------
+    def can_hoist(self) -> bool:
+        return self.bn_mode == _lib.BN_EVAL and self.precision == _lib.PREC_BF16
+
+    def hoist_layer0(self, desc, kpts, scores, n_img, K, hw):
+        """Residual stream entering GNN layer 1 for every image of a record store: (n_img, K, 256) f32.  Layer 0 is
+        a self layer, so with running BatchNorm statistics this part of the forward pass does not depend on the
+        pair and is done once per image (desc (n,256,ldk), kpts (n,kcap,2), scores (n,kcap))."""
+        L = lib()
+        dev = self.device
+        nbytes = L.sfm_superglue_workspace_bytes(n_img, K, K, self.precision, 1)
+        ws = self.handle.workspace("sg", nbytes)
+        store = torch.empty(n_img, K, 256, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(L.sfm_superglue_hoist_layer0(self.handle.h, ptr(desc), ptr(kpts), ptr(scores), desc.shape[-1],
+                                               kpts.shape[-2], n_img, K, hw[0], hw[1], self.precision, ptr(store),
+                                               ptr(ws), ws.numel(), stream_ptr(dev)))
+        return store
+
+    def match_hoisted(self, store0, idx0, store1, idx1, B, K0, K1):
+        """Layers 1..17 + optimal transport + mutual matches for B pairs gathered from hoisted stores."""
+        L = lib()
+        dev = self.device
+        nbytes = L.sfm_superglue_workspace_bytes(B, K0, K1, self.precision, 1)
+        ws = self.handle.workspace("sg", nbytes)
+        m0 = torch.empty(B, K0, dtype=torch.int64, device=dev)
+        m1 = torch.empty(B, K1, dtype=torch.int64, device=dev)
+        s0 = torch.empty(B, K0, dtype=torch.float32, device=dev)
+        s1 = torch.empty(B, K1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(L.sfm_superglue_forward_hoisted(self.handle.h, ptr(store0), store0.shape[1], ptr(idx0), ptr(store1),
+                                                  store1.shape[1], ptr(idx1), B, K0, K1, self.sinkhorn_iterations,
+                                                  self.match_threshold, self.precision, ptr(m0), ptr(m1), ptr(s0),
+                                                  ptr(s1), ptr(ws), ws.numel(), stream_ptr(dev)))
+        return m0, m1, s0, s1, ws
+
     def tap(self, B, K0, K1, which, ws, chunk_groups=1):
         p, cnt = C.c_void_p(), C.c_size_t()
         check(lib().sfm_superglue_tap(B, K0, K1, self.precision, chunk_groups, which, ptr(ws), ws.numel(),
