@@ -221,6 +221,20 @@ SFM_API int sfm_compact_matches(const int64_t* matches0, int B, int K0, uint32_t
 SFM_API int sfm_pack_tables(const uint32_t* tables, int n_pairs, int kcap, const int* lengths, const int64_t* offsets,
                             uint32_t* out, void* stream);
 
+/* Post-match consumer generate_sparse_depth_from_colmap (dataset/simple_sfm_dataset_utils.py:195-231, with
+ * coords_world_to_cam / coords_cam_to_film / coords_film_to_pixel, utils/coord_conversion.py:61-97,138-159), all
+ * cameras of one image size in one call, float64 like the reference.
+ *   xyz (n_points,3); entries e = (entry_cam[e], entry_point[e]): point visible in camera, a camera's points in model
+ *   order; extrinsics (n_cams,12) rows of world-to-camera [R|t]; intrinsics (n_cams,4) = f_x, f_y, c_x, c_y relative
+ *   to the image size; depth out (n_cams,W,H), -1 where empty, on a pixel hit by several points the LAST entry's
+ *   depth (the reference's indexed write); bounds out (n_cams,2) = min / max depth over every in-frustum point
+ *   (+inf / 0 when none); winner_ws n_cams*W*H int64 scratch; error_flag = 1 when a point lands on x == W or
+ *   y == H (the reference raises IndexError there). */
+SFM_API int sfm_sparse_depth(const double* xyz, int n_points, const int* entry_cam, const int* entry_point,
+                             long long n_entries, const double* extrinsics, const double* intrinsics, int n_cams,
+                             int W, int H, double* depth, double* bounds, long long* winner_ws, int* error_flag,
+                             void* stream);
+
 /* SimpleMatcher.match_two_way(_cuda) (simple_matcher.py:66-114): desc (256,N) / (256,M) unit f32.
  * out (3, min(N,M)) f32 rows [i, j, dist], count = L. */
 SFM_API size_t sfm_simple_match_workspace_bytes(int N, int M);

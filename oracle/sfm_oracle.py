@@ -412,3 +412,67 @@ def colmap_match_blob(id1: int, id2: int, matches: np.ndarray) -> Tuple[int, int
     m = matches[:, [1, 0]] if id1 > id2 else matches
     m = np.ascontiguousarray(m)
     return colmap_pair_id(id1, id2), m.shape[0], m.shape[1], m.tobytes()
+
+
+# --------------------------------------------------------------------------------------
+# Post-match consumer: sparse depth from a COLMAP sparse model
+# (simple_sfm/dataset/simple_sfm_dataset_utils.py:147-261)
+# --------------------------------------------------------------------------------------
+
+def read_points3d_bin(path: str) -> List[Tuple[np.ndarray, float, np.ndarray]]:
+    """points3D.bin -> [(xyz, error, image_ids)] in file order.  colmap_utils/read_write_colmap_data.py:336-363."""
+    import struct
+    out = []
+    with open(path, "rb") as fid:
+        (n,) = struct.unpack("<Q", fid.read(8))
+        for _ in range(n):
+            rec = struct.unpack("<QdddBBBd", fid.read(43))
+            (tl,) = struct.unpack("<Q", fid.read(8))
+            tr = struct.unpack("<" + "ii" * tl, fid.read(8 * tl))
+            out.append((np.array(rec[1:4]), float(rec[7]), np.array(tr[0::2], dtype=np.int64)))
+    return out
+
+
+def simple_sfm_json_cameras(views: dict):
+    """cameras/camera_multiple.py:212-276: per view sorted by id -> (w2c 4x4, K 3x3, [W, H], id, file_path).
+    K[1][2] is c_x as in the reference (:252)."""
+    cams = []
+    for view in sorted(views["frames"], key=lambda item: item["id"]):
+        k = view["intrinsic"]
+        c2w = np.array(view["transform_matrix"])
+        c2w[2, :] *= 1
+        c2w = c2w[[1, 0, 2, 3], :]
+        c2w[0:3, 1] *= -1
+        c2w[0:3, 2] *= -1
+        K = np.array([[k["f_x"], 0, k["c_x"]], [0, k["f_y"], k["c_x"]], [0, 0, 1]], dtype=np.float64)
+        cams.append((np.linalg.inv(c2w), K, [k["original_resolution_x"], k["original_resolution_y"]],
+                     int(view["id"]), view["file_path"]))
+    return cams
+
+
+def sparse_depth_for_camera(points, w2c: np.ndarray, K: np.ndarray, size, camera_id: int, scale: float = 1,
+                            error_threshold: float = 2.0):
+    """One iteration of the camera loop (simple_sfm_dataset_utils.py:195-233) -> (sparse_depth (1,W,H) f64,
+    mask (1,W,H) bool, points_bounds).  Projection: utils/coord_conversion.py:61-97, 138-159."""
+    W, H = int(size[0] // scale), int(size[1] // scale)
+    sel = [xyz for xyz, err, image_ids in points if error_threshold > err and camera_id + 1 in image_ids]   # :204-209
+    depth = np.zeros((W, H, 1), np.float64) - 1
+    bounds = [-1, 1]
+    if sel:
+        p = np.array(sel, np.float64)
+        cam = p @ w2c[:3, :3].T + w2c[:3, 3]                                  # world_to_cam
+        z = cam[:, 2:]
+        den = np.where(z >= 0, np.maximum(z, 1e-6), np.minimum(z, -1e-6))      # cam_to_film
+        film = cam[:, :2] / den
+        pix = film * np.diagonal(K[:2, :2]) + K[:2, 2]                         # film_to_pixel
+        px = np.concatenate([pix, z], 1) * np.array([[W, H, 1]], np.float64)   # :211
+        m = (px[:, 0] >= 0) & (px[:, 0] <= W) & (px[:, 1] >= 0) & (px[:, 1] <= H) & (px[:, 2] >= 0)
+        px = px[m]
+        xy = px[:, :2].astype(np.int64)                                        # .long() truncation
+        if len(px):
+            if (xy[:, 0] >= W).any() or (xy[:, 1] >= H).any():
+                raise IndexError("projected point on the x == W / y == H edge")
+            for (x, y), d in zip(xy, px[:, 2]):                                # indexed write: the last point wins
+                depth[x, y, 0] = d
+            bounds = [px[:, 2].min(), px[:, 2].max()]
+    return depth.transpose(2, 0, 1), (depth != -1).transpose(2, 0, 1), bounds

@@ -35,3 +35,11 @@ def install_as_simple_sfm() -> None:
     if "simple_sfm.models" not in sys.modules:
         sys.modules["simple_sfm.models"] = models
     pkg.matchers = matchers
+    # post-match consumer: only the one function is replaced -- the reference module holds other,
+    # out-of-scope generators that must stay reachable
+    from .dataset import simple_sfm_dataset_utils as depth_utils
+    try:
+        ref_utils = importlib.import_module("simple_sfm.dataset.simple_sfm_dataset_utils")
+        ref_utils.generate_sparse_depth_from_colmap = depth_utils.generate_sparse_depth_from_colmap
+    except Exception:
+        sys.modules.setdefault("simple_sfm.dataset.simple_sfm_dataset_utils", depth_utils)

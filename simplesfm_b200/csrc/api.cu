@@ -651,6 +651,16 @@ int sfm_pack_tables(const uint32_t* tables, int n_pairs, int kcap, const int* le
   return pack_tables(tables, n_pairs, kcap, lengths, (const long long*)offsets, out, (cudaStream_t)stream);
 }
 
+int sfm_sparse_depth(const double* xyz, int n_points, const int* entry_cam, const int* entry_point, long long n_entries,
+                     const double* extrinsics, const double* intrinsics, int n_cams, int W, int H, double* depth,
+                     double* bounds, long long* winner_ws, int* error_flag, void* stream) {
+  SFM_REQUIRE(n_cams >= 0 && W > 0 && H > 0 && n_points >= 0 && n_entries >= 0, "sfm_sparse_depth: bad dims");
+  SFM_REQUIRE(n_cams == 0 || (extrinsics && intrinsics && depth && bounds && winner_ws && error_flag), "sfm_sparse_depth: NULL argument");
+  SFM_REQUIRE(n_entries == 0 || (xyz && entry_cam && entry_point), "sfm_sparse_depth: NULL entries");
+  return sparse_depth_project(xyz, entry_cam, entry_point, n_entries, extrinsics, intrinsics, n_cams, W, H, depth,
+                              bounds, winner_ws, error_flag, (cudaStream_t)stream);
+}
+
 // ---- kernel-level test hooks of the tcgen05 path ------------------------------------------------
 int sfm_tc_gemm(sfm_handle_t h, const void* A, const void* A2, const void* W, int M, int N, int K, int K1,
                 const float* bias, float alpha, int relu, void* out_bf16, float* out_f32, int accumulate,

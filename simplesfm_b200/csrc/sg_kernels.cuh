@@ -67,6 +67,11 @@ int sinkhorn_write_Z(const SinkhornArgs& a, float* Z, cudaStream_t st);
 int log_sinkhorn_general(const float* Z, const float* log_mu, const float* log_nu, int B, int m, int n, int iters,
                          float* out, float* u, float* v, cudaStream_t st);
 
+// sparse depth maps from a COLMAP sparse model (sparse_depth.cu): depth [n_cams, W, H] f64 (-1 = empty)
+int sparse_depth_project(const double* xyz, const int* entry_cam, const int* entry_point, long long n_entries,
+                         const double* extrinsics, const double* intrinsics, int n_cams, int W, int H, double* depth,
+                         double* bounds, long long* winner_ws, int* error_flag, cudaStream_t st);
+
 // (L,2) uint32 match-table compaction per pair: rows [i, matches0[i]] for matches0[i] > -1
 int compact_matches(const long long* matches0, int B, int N, unsigned* tables, int* lengths, cudaStream_t st);
 // flatten per-pair (kcap, 2) tables into one (sum lengths, 2) array; offsets = exclusive prefix sum of lengths

@@ -281,8 +281,69 @@ def golden_module_functions():
     npz("module_functions", **save)
 
 
+def golden_sparse_depth():
+    """Post-match consumer `generate_sparse_depth_from_colmap` (dataset/simple_sfm_dataset_utils.py:147-261): a tiny
+    synthetic dataset (views_data.json + a COLMAP sparse model written with the reference's own writer) through the
+    unmodified reference function; the input files are stored byte for byte, the outputs as arrays."""
+    import json
+    import shutil
+    from simple_sfm.colmap_utils import read_write_colmap_data as RW
+    from simple_sfm.dataset import simple_sfm_dataset_utils as U
+    rng = np.random.RandomState(7)
+    root = os.path.join(TMP, "depth_ds")
+    os.makedirs(os.path.join(root, "colmap", "sparse"))
+    n_cam, n_pts, Wd, Hd = 6, 400, 64, 48
+    frames = []
+    for i in range(n_cam):
+        ang = 0.35 * (i - n_cam / 2)
+        c, s_ = np.cos(ang), np.sin(ang)
+        R = np.array([[c, 0, s_], [0, 1, 0], [-s_, 0, c]])          # camera-to-world rotation (before the json quirks)
+        t = np.array([-2.5 * s_, 0.1 * i, -2.5 * c])
+        c2w = np.eye(4)
+        c2w[:3, :3], c2w[:3, 3] = R, t
+        # undo what from_simple_sfm_json does (camera_multiple.py:242-247) so that the camera looks at the origin
+        m = c2w.copy()
+        m[0:3, 1] *= -1
+        m[0:3, 2] *= -1
+        m = m[[1, 0, 2, 3], :]
+        frames.append({"id": (i * 5) % n_cam if False else i, "file_path": f"images/view_{i:02d}.png",
+                       "transform_matrix": m.tolist(),
+                       "intrinsic": {"f_x": 0.9 + 0.01 * i, "f_y": 1.2, "c_x": 0.5, "c_y": 0.47,
+                                     "original_resolution_x": Wd, "original_resolution_y": Hd}})
+    frames = [frames[k] for k in (3, 0, 5, 1, 4, 2)]                 # the reference sorts by id
+    with open(os.path.join(root, "views_data.json"), "w") as fh:
+        json.dump({"frames": frames}, fh)
+    pts = {}
+    for k in range(n_pts):
+        xyz = rng.uniform(-0.9, 0.9, 3) * np.array([1.0, 0.7, 1.0])
+        n_obs = rng.randint(1, 5)
+        ids = rng.randint(1, n_cam + 1, size=n_obs)                 # may repeat an image (membership test in the reference)
+        pts[k + 10] = RW.Point3D(id=k + 10, xyz=xyz, rgb=np.array([1, 2, 3]), error=float(rng.uniform(0.1, 3.5)),
+                                 image_ids=ids, point2D_idxs=rng.randint(0, 50, size=n_obs))
+    cams = {1: RW.Camera(id=1, model="SIMPLE_PINHOLE", width=Wd, height=Hd, params=np.array([50.0, 32.0, 24.0]))}
+    ims = {i + 1: RW.BaseImage(id=i + 1, qvec=np.array([1.0, 0, 0, 0]), tvec=np.zeros(3), camera_id=1,
+                               name=f"view_{i:02d}.png", xys=np.zeros((1, 2)), point3D_ids=np.array([-1]))
+           for i in range(n_cam)}
+    RW.write_model(cams, ims, pts, os.path.join(root, "colmap", "sparse"), ext="bin")
+    save = {"views_json": np.frombuffer(open(os.path.join(root, "views_data.json"), "rb").read(), np.uint8)}
+    for name in ("cameras.bin", "images.bin", "points3D.bin"):
+        save["model_" + name.replace(".", "_")] = np.frombuffer(
+            open(os.path.join(root, "colmap", "sparse", name), "rb").read(), np.uint8)
+    for tag, scale, thr in (("s1", 1, 2.0), ("s2", 2, 3.0)):
+        work = os.path.join(TMP, "depth_run_" + tag)
+        shutil.copytree(root, work)
+        U.generate_sparse_depth_from_colmap(work, scale=scale, error_threshold=thr)
+        out = json.load(open(os.path.join(work, "views_data.json")))
+        save[f"{tag}_paths"] = np.array([f["sparse_depth_path"] for f in out["frames"]])
+        for f in out["frames"]:
+            d = np.load(os.path.join(work, f["sparse_depth_path"]), allow_pickle=True).item()
+            save[f"{tag}_depth_{f['id']}"] = d["sparse_depth"]
+            save[f"{tag}_mask_{f['id']}"] = d["sparse_depth_mask"]
+    npz("sparse_depth", **save)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (golden_superpoint, golden_superglue, golden_matcher, golden_module_functions):
+    for fn in (golden_superpoint, golden_superglue, golden_matcher, golden_module_functions, golden_sparse_depth):
         if not only or fn.__name__ in only:
             fn()
