@@ -101,7 +101,7 @@ def test_cuda_path_matches_reference_golden(tmp_path):
 
 @pytest.mark.gpu
 def test_cuda_path_matches_oracle_with_collisions():
-    """40 000 points into 12 cameras of 48 x 36 pixels: almost every pixel is hit several times, so the
+    """40 000 points into 12 cameras of 48 x 36 pixels: most pixels are hit several times, so the
     last-point-wins rule of the reference's indexed write decides nearly every value."""
     from simplesfm_b200.dataset import simple_sfm_dataset_utils as U
     rng = np.random.RandomState(3)
@@ -132,7 +132,7 @@ def test_cuda_path_matches_oracle_with_collisions():
         np.testing.assert_allclose(depth[i], want[0], rtol=1e-12, atol=1e-12)
         np.testing.assert_allclose(bounds[i], wb, rtol=1e-12)
         filled += int(mask.sum())
-    assert filled > 0.8 * n_cam * W * H
+    assert filled > 0.6 * n_cam * W * H and len(ecam) > 3 * filled      # most pixels are contested
 
 
 @pytest.mark.gpu
