@@ -35,9 +35,69 @@ namespace tc {
 namespace {
 
 constexpr int KV_STAGES = 3;
+
+#ifdef SFM_ATT_TRACE
+// debug build only (tools/att_trace.py): clock64 time stamps of CTA 0 for K/V steps [TRACE_G0, TRACE_G0 + TRACE_NG)
+constexpr int TRACE_G0 = 64, TRACE_NG = 24;
+__device__ long long g_att_trace[TRACE_NG * 64];
+#define ATT_TRACE(g, ev)                                                                              \
+  do {                                                                                                \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (g) >= TRACE_G0 && (g) < TRACE_G0 + TRACE_NG)   \
+      g_att_trace[((g) - TRACE_G0) * 64 + (ev)] = clock64();                                          \
+  } while (0)
+#else
+#define ATT_TRACE(g, ev) do { } while (0)
+#endif
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, 128-byte swizzled rows
 // warp 0: TMA producer; warps 1..NT: one MMA issuer per query tile; then NT softmax warpgroups
 template <int NT> struct AttCfg { static constexpr int SW0 = 1 + NT; static constexpr int THREADS = (1 + NT) * 32 + NT * 128; };
+
+__device__ __forceinline__ void att_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// Unit epilogue of one softmax thread (out of line: its 64 + 32 live registers must not weigh on the allocation of
+// the K/V loop): O row from TMEM -> 1 / l -> bf16.  A whole tile leaves as ONE coalesced TMA store from a swizzled
+// staging tile: a thread owns a row, so direct stores touch 32 different 128-byte lines per instruction and the LSU
+// back-pressure keeps the tile's warps away from the MUFU for ~1 700 clocks per unit.
+__device__ __noinline__ void att_epilogue(uint32_t o_addr, float inv, bool whole, bool row_ok, int t, int wg_tid,
+                                          int row_in_tile, uint32_t stage, const CUtensorMap* map_out, int col0,
+                                          long long row0, __nv_bfloat16* out) {
+  uint32_t o[64];
+  tmem_ld_32x32(o_addr, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+  tmem_ld_32x32(o_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+  tmem_wait_ld();
+  tc_fence_before();   // O_t is in registers: the next unit's first P V may overwrite it
+  auto chunk = [&](int i) {   // 8 output channels of this row as bf16
+    return make_uint4(pack_bf16(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv),
+                      pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv),
+                      pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv),
+                      pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv));
+  };
+  if (whole) {
+    if (wg_tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous unit's store has left smem
+    att_bar_sync(1 + t, 128);
+    const uint32_t row_base = stage + row_in_tile * 128;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const uint4 v = chunk(i);
+      st_shared_v4(row_base + ((i ^ (row_in_tile & 7)) << 4), v.x, v.y, v.z, v.w);
+    }
+    fence_proxy_async();
+    att_bar_sync(1 + t, 128);
+    if (wg_tid == 0) {
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                       reinterpret_cast<uint64_t>(map_out)),
+                   "r"(stage), "r"(col0), "r"((int)row0)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  } else if (row_ok) {   // ragged tile: the rows past Nq belong to another pair
+    uint4* d4 = reinterpret_cast<uint4*>(out + (row0 + row_in_tile) * 256 + col0);
+#pragma unroll
+    for (int i = 0; i < 8; i++) d4[i] = chunk(i);
+  }
+}
 
 struct AttBars {
   uint64_t q_full[2], q_empty[2];
@@ -72,18 +132,21 @@ __device__ __forceinline__ Unit decode_unit(const TcAttn& p, int u, int units0, 
 
 template <int NT>
 __global__ void __launch_bounds__(AttCfg<NT>::THREADS, 1)
-tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units0, int qt0, int qt1, int n_units) {
+tc_attention_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap map_out, TcAttn p,
+                    int units0, int qt0, int qt1, int n_units) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                             // 2 buffers x NT tiles
   uint8_t* sK = smem + 2 * NT * TILE_BYTES;       // KV_STAGES tiles
   uint8_t* sV = sK + KV_STAGES * TILE_BYTES;      // KV_STAGES tiles
-  AttBars* bars = reinterpret_cast<AttBars*>(sV + KV_STAGES * TILE_BYTES);
+  uint8_t* sO = sV + KV_STAGES * TILE_BYTES;      // NT output staging tiles (128 rows x 128 B, 128-byte swizzle)
+  AttBars* bars = reinterpret_cast<AttBars*>(sO + NT * TILE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map);
+    tma_prefetch_desc(&map_out);
     for (int q = 0; q < 2; q++) {
       mbar_init(&bars->q_full[q], 1);
       mbar_init(&bars->q_empty[q], NT);
@@ -173,19 +236,23 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
         Cursor nxt = cur;
         advance(nxt);
         const bool cur_first = cur.j == 0, cur_last = cur.j + 1 == cur.n_kv;
+        ATT_TRACE(g, 48 + t * 6 + 0);
         if (nxt.valid) {
           // S of step g+1 (next K/V tile of this unit, or tile 0 of the next unit with its own Q buffer): issued as
           // soon as the softmax group holds S_t(g) in registers, so it overlaps the exponentials of step g
           const int s1 = (g + 1) % KV_STAGES;
           if (nxt.j == 0) mbar_wait(&bars->q_full[nxt.it & 1], (nxt.it >> 1) & 1);
           mbar_wait(&bars->kv_full[s1], ((g + 1) / KV_STAGES) & 1);
+          ATT_TRACE(g, 48 + t * 6 + 1);
           mbar_wait(&bars->s_free[t], g & 1);
+          ATT_TRACE(g, 48 + t * 6 + 2);
           tc_fence_after();
           issue_s(nxt.it & 1, s1);
         }
         // every S MMA of this tile that reads this unit's Q buffer has been issued
         if (cur_last) umma_commit(&bars->q_empty[cur.it & 1]);
         mbar_wait(&bars->p_full[t], g & 1);
+        ATT_TRACE(g, 48 + t * 6 + 3);
         tc_fence_after();
         const uint64_t vd = umma_desc_advance(v_desc0, (g % KV_STAGES) * TILE_BYTES);
 #pragma unroll
@@ -223,7 +290,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
     bool pend = false, any_pend = false, bad = false;
 
     for (int j = 0; j < n_kv; j++, g++) {
+      ATT_TRACE(g, (warp - AttCfg<NT>::SW0) * 6 + 0);
       mbar_wait(&bars->s_full[t], g & 1);
+      ATT_TRACE(g, (warp - AttCfg<NT>::SW0) * 6 + 1);
       tc_fence_after();
       const int valid = min(128, Nk - j * 128);  // columns of this tile that are real keys
       const bool waited = any_pend;
@@ -294,13 +363,16 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_free[t]);   // S_t is in registers: the tensor pipe may overwrite it
+      ATT_TRACE(g, (warp - AttCfg<NT>::SW0) * 6 + 2);
       exp32(1);
       mx = fmax3(mx, max32(32), max32(64));
       mx = fmaxf(mx, max32(96));
       if (j > 0 && !waited) {
         // P V (j-1) must have consumed P_t before it is overwritten; by now that MMA (issue + 256 tensor clocks +
         // commit) has had 64 exponentials of time
+        ATT_TRACE(g, (warp - AttCfg<NT>::SW0) * 6 + 3);
         mbar_wait(&bars->o_full[t], (g - 1) & 1);
+        ATT_TRACE(g, (warp - AttCfg<NT>::SW0) * 6 + 4);
         tc_fence_after();
       }
       tmem_st_32x32(lane_addr + COL_P + t * 64, pk);
@@ -323,34 +395,25 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, TcAttn p, int units
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full[t]);
+      ATT_TRACE(g, (warp - AttCfg<NT>::SW0) * 6 + 5);
     }
     mbar_wait(&bars->o_full[t], (g - 1) & 1);
+    ATT_TRACE(g, (warp - AttCfg<NT>::SW0) * 6 + 3);   // (unit epilogue: the next step has no P V wait, its slots are free)
     tc_fence_after();
     {
-      uint32_t o[64];
-      tmem_ld_32x32(lane_addr + COL_O + t * 64, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
-      tmem_ld_32x32(lane_addr + COL_O + t * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
-      tmem_wait_ld();
-      tc_fence_before();   // O_t is in registers: the next unit's first P V may overwrite it
-      if (qi < w.Nq) {
-        const float inv = 1.f / l_run;
-        __nv_bfloat16* dst = p.out + (w.qrow + t * 128 + row_in_tile) * 256 + w.head * 64;
-        uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-          d4[i] = make_uint4(pack_bf16(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv),
-                             pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv),
-                             pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv),
-                             pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv));
-        if (bad && p.redo != nullptr) {   // (practically never) hand the row to the exact recomputation
-          const int slot = atomicAdd(p.redo, 1);
-          if (slot < p.redo_cap)
-            reinterpret_cast<int4*>(p.redo + 4)[slot] =
-                make_int4((int)(w.qrow + t * 128 + row_in_tile), w.head, (int)w.krow, Nk);
-        }
+      const bool whole = p.tma_out && w.qblk * (NT * 128) + t * 128 + 128 <= w.Nq;
+      att_epilogue(lane_addr + COL_O + t * 64, 1.f / l_run, whole, qi < w.Nq, t, (warp - AttCfg<NT>::SW0 - 4 * t) * 32 + lane,
+                   row_in_tile, smem_u32(sO + t * TILE_BYTES), &map_out, w.head * 64, w.qrow + t * 128, p.out);
+      ATT_TRACE(g, (warp - AttCfg<NT>::SW0) * 6 + 4);
+      if (qi < w.Nq && bad && p.redo != nullptr) {   // (practically never) hand the row to the exact recomputation
+        const int slot = atomicAdd(p.redo, 1);
+        if (slot < p.redo_cap)
+          reinterpret_cast<int4*>(p.redo + 4)[slot] =
+              make_int4((int)(w.qrow + t * 128 + row_in_tile), w.head, (int)w.krow, Nk);
       }
     }
     }  // units
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // (only the storing threads have groups in flight)
   }
   tc_fence_before();
   __syncthreads();
@@ -391,14 +454,14 @@ __global__ void __launch_bounds__(256) att_redo_kernel(const __nv_bfloat16* __re
 }
 
 template <int NT>
-int launch_att(const TcAttn& p, const CUtensorMap& map, int num_sms, cudaStream_t st) {
+int launch_att(const TcAttn& p, const CUtensorMap& map, const CUtensorMap& map_out, int num_sms, cudaStream_t st) {
   const int qt0 = cdiv(p.Nq[0], NT * 128), qt1 = p.Nq[1] > 0 ? cdiv(p.Nq[1], NT * 128) : 0;
   const int units0 = p.B * 4 * qt0, units1 = p.B * 4 * qt1;
   const int n_units = units0 + units1;
-  const size_t smem = (size_t)(2 * NT + 2 * KV_STAGES) * TILE_BYTES + sizeof(AttBars) + 1024;
+  const size_t smem = (size_t)(3 * NT + 2 * KV_STAGES) * TILE_BYTES + sizeof(AttBars) + 1024;
   SFM_SMEM_OPT_IN(tc_attention_kernel<NT>, smem);
   const int grid = std::min(n_units, num_sms);
-  tc_attention_kernel<NT><<<grid, AttCfg<NT>::THREADS, smem, st>>>(map, p, units0, qt0, qt1 > 0 ? qt1 : 1, n_units);
+  tc_attention_kernel<NT><<<grid, AttCfg<NT>::THREADS, smem, st>>>(map, map_out, p, units0, qt0, qt1 > 0 ? qt1 : 1, n_units);
   SFM_LAUNCH_CHECK();
   if (p.redo != nullptr) {
     att_redo_kernel<<<1, 256, 0, st>>>(p.qkv, p.out, p.redo, p.redo_cap);
@@ -413,15 +476,25 @@ int tc_attention(const TcAttn& p, int num_sms, cudaStream_t st) {
   SFM_REQUIRE(p.B > 0 && p.Nq[0] > 0 && p.Nk[0] > 0 && p.Nq[1] >= 0, "tc_attention: bad dims");
   CUtensorMap map;
   SFM_TRY(get_tmap_bf16(p.tmaps, &map, p.qkv, p.rows_total, 768, 768, 128));
+  CUtensorMap map_out;
+  SFM_TRY(get_tmap_bf16(p.tmaps, &map_out, p.out, p.rows_total, 256, 256, 128));
   // tuning knobs are read from the environment once per process (read-only afterwards)
   static const int nt = getenv("SFM_ATT_NT") ? atoi(getenv("SFM_ATT_NT")) : 2;
   static const int stagger = getenv("SFM_ATT_STAGGER") ? atoi(getenv("SFM_ATT_STAGGER")) : 1;
+  static const int tma_out = getenv("SFM_ATT_TMA_OUT") ? atoi(getenv("SFM_ATT_TMA_OUT")) : 1;
   TcAttn q = p;
   q.stagger = stagger;
+  q.tma_out = tma_out;
   SFM_REQUIRE(num_sms > 0, "tc_attention: bad SM count");
-  if (nt == 1) return launch_att<1>(q, map, num_sms, st);
-  return launch_att<2>(q, map, num_sms, st);
+  if (nt == 1) return launch_att<1>(q, map, map_out, num_sms, st);
+  return launch_att<2>(q, map, map_out, num_sms, st);
 }
 
 }  // namespace tc
 }  // namespace sfm
+
+#ifdef SFM_ATT_TRACE
+extern "C" __attribute__((visibility("default"))) int sfm_debug_att_trace(long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, sfm::tc::g_att_trace, sizeof(long long) * n);
+}
+#endif

@@ -76,6 +76,7 @@ struct TcAttn {
   int B = 0;
   int Nq[2] = {0, 0}, Nk[2] = {0, 0};
   long long q_row0[2] = {0, 0}, k_row0[2] = {0, 0};
+  int tma_out = 1;   // whole output tiles leave through a swizzled staging tile and one TMA store
   int stagger = 1;   // tile 1 of a CTA runs half a K/V step behind tile 0 (ping-pong on the MUFU pipe)
   TmapCache* tmaps = nullptr;   // the handle's tensor-map cache (optional)
   // exact-recomputation list (handle-owned, zero on entry, left zero): redo[0] = count, entries int4 from redo + 4
