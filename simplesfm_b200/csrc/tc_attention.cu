@@ -120,8 +120,13 @@ __device__ __forceinline__ Unit decode_unit(const TcAttn& p, int u, int units0, 
   }
   const int qts = w.side == 0 ? qt0 : qt1;
   w.head = u & 3;
-  w.qblk = (u >> 2) % qts;
-  w.b = (u >> 2) / qts;
+  if ((qts & (qts - 1)) == 0) {   // the usual case (2048 keypoints: 8 query blocks); a division costs ~250 clocks per unit
+    w.qblk = (u >> 2) & (qts - 1);
+    w.b = (u >> 2) >> (31 - __clz(qts));
+  } else {
+    w.qblk = (u >> 2) % qts;
+    w.b = (u >> 2) / qts;
+  }
   w.Nq = p.Nq[w.side];
   w.Nk = p.Nk[w.side];
   w.qrow = p.q_row0[w.side] + (long long)w.b * w.Nq + w.qblk * (NT * 128);
@@ -200,7 +205,12 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
     // tiles share only the K/V ring and the Q buffers, released when BOTH issuers' MMAs on them have completed
     // (kv_empty / q_empty count NT; tcgen05.commit tracks the issuing thread's own MMAs).
     const int t = warp - 1;
-    if (lane == 0 && blockIdx.x < n_units) {
+    // The WHOLE warp runs this loop and one elected lane issues: descriptors, TMEM addresses and barrier addresses then
+    // live in uniform registers.  Under `if (lane == 0)` they are per-thread values and every tcgen05.mma is wrapped
+    // in an ELECT / R2UR.BROADCAST / branch sequence (~85 clocks per MMA: the eight P V MMAs of a step took 700
+    // clocks to issue, which put S (g+1) at 70 % of step g).
+    if (blockIdx.x < n_units) {
+      const bool leader = elect_one_sync();
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);  // S = Q K^T : B = K tile, K-major
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);   // O = P V   : B = V tile, MN-major
       const uint64_t q_desc0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
@@ -210,11 +220,13 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
       auto issue_s = [&](int qb, int stage) {
         const uint64_t ad = umma_desc_advance(q_desc0, (qb * NT + t) * TILE_BYTES);
         const uint64_t bd = umma_desc_advance(k_desc0, stage * TILE_BYTES);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-          umma_ss(tmem + COL_S + t * 128, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc_s,
-                  k != 0);
-        umma_commit(&bars->s_full[t]);
+          for (int k = 0; k < 4; k++)
+            umma_ss(tmem + COL_S + t * 128, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc_s,
+                    k != 0);
+          umma_commit(&bars->s_full[t]);
+        }
       };
       struct Cursor { int u, it, j, n_kv; bool valid; };
       auto advance = [&](Cursor& c) {
@@ -250,17 +262,22 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
           issue_s(nxt.it & 1, s1);
         }
         // every S MMA of this tile that reads this unit's Q buffer has been issued
-        if (cur_last) umma_commit(&bars->q_empty[cur.it & 1]);
+        if (cur_last && leader) umma_commit(&bars->q_empty[cur.it & 1]);
         mbar_wait(&bars->p_full[t], g & 1);
         ATT_TRACE(g, 48 + t * 6 + 3);
         tc_fence_after();
         const uint64_t vd = umma_desc_advance(v_desc0, (g % KV_STAGES) * TILE_BYTES);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 8; k++)  // 16 keys per step: 16 V rows = 2048 bytes, P advances 8 columns
-          umma_ts(tmem + COL_O + t * 64, tmem + COL_P + t * 64 + k * 8, umma_desc_advance(vd, k * 2048), idesc_o,
-                  (cur_first ? 0 : 1) | k);
-        umma_commit(&bars->o_full[t]);
-        umma_commit(&bars->kv_empty[g % KV_STAGES]);   // this tile is done with K/V slot g (S_t(g) and P V_t(g))
+          for (int k = 0; k < 8; k++)  // 16 keys per step: 16 V rows = 2048 bytes, P advances 8 columns
+            umma_ts(tmem + COL_O + t * 64, tmem + COL_P + t * 64 + k * 8, umma_desc_advance(vd, k * 2048), idesc_o,
+                    (cur_first ? 0 : 1) | k);
+          ATT_TRACE(g, 48 + t * 6 + 4);
+          umma_commit(&bars->o_full[t]);
+          umma_commit(&bars->kv_empty[g % KV_STAGES]);   // this tile is done with K/V slot g (S_t(g) and P V_t(g))
+          ATT_TRACE(g, 48 + t * 6 + 5);
+        }
+        __syncwarp();
         cur = nxt;
       }
     }

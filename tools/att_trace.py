@@ -37,4 +37,4 @@ for g in range(NG):
             line += f"{nm} {vals}  "
         print(line)
         i = 48 + t * 6
-        print(f"          issuer: top {r[i] - base}, kv_full(g+1) {r[i + 1] - base}, S(g+1) issue {r[i + 2] - base}, PV(g) issue {r[i + 3] - base}")
+        print(f"          issuer: top {r[i] - base}, kv_full(g+1) {r[i + 1] - base}, S(g+1) issue {r[i + 2] - base}, PV(g) issue {r[i + 3] - base}, PV issued {r[i + 4] - base}, committed {r[i + 5] - base}")
