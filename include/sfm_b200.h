@@ -221,6 +221,12 @@ SFM_API int sfm_compact_matches(const int64_t* matches0, int B, int K0, uint32_t
 SFM_API int sfm_pack_tables(const uint32_t* tables, int n_pairs, int kcap, const int* lengths, const int64_t* offsets,
                             uint32_t* out, void* stream);
 
+/* Pair schedule of Matcher.match_frames without a filter (matcher.py:143-144, itertools.combinations(ids, 2)):
+ * entries [first, first + count) of the lexicographic list of (i < j), 0 <= i < j < n_images, as two device int32
+ * arrays of image positions -- the index arrays sfm_superglue_forward takes; a rank of the multi-GPU partition
+ * generates exactly its own range. */
+SFM_API int sfm_pair_list(int n_images, long long first, long long count, int* idx0, int* idx1, void* stream);
+
 /* Post-match consumer generate_sparse_depth_from_colmap (dataset/simple_sfm_dataset_utils.py:195-231, with
  * coords_world_to_cam / coords_cam_to_film / coords_film_to_pixel, utils/coord_conversion.py:61-97,138-159), all
  * cameras of one image size in one call, float64 like the reference.

@@ -651,6 +651,13 @@ int sfm_pack_tables(const uint32_t* tables, int n_pairs, int kcap, const int* le
   return pack_tables(tables, n_pairs, kcap, lengths, (const long long*)offsets, out, (cudaStream_t)stream);
 }
 
+int sfm_pair_list(int n_images, long long first, long long count, int* idx0, int* idx1, void* stream) {
+  const long long total = (long long)n_images * (n_images - 1) / 2;
+  SFM_REQUIRE(n_images >= 0 && first >= 0 && count >= 0 && first + count <= total, "sfm_pair_list: range outside the %lld pairs of %d images", total, n_images);
+  SFM_REQUIRE(count == 0 || (idx0 && idx1), "sfm_pair_list: NULL output");
+  return pair_list_range(n_images, first, count, idx0, idx1, (cudaStream_t)stream);
+}
+
 int sfm_sparse_depth(const double* xyz, int n_points, const int* entry_cam, const int* entry_point, long long n_entries,
                      const double* extrinsics, const double* intrinsics, int n_cams, int W, int H, double* depth,
                      double* bounds, long long* winner_ws, int* error_flag, void* stream) {

@@ -333,7 +333,7 @@ int conv1a_f32(const float* img, const float* w9, const float* bias, float* out,
 }
 
 int maxpool2_nhwc_f32(const float* in, float* out, int n_img, int H, int W, int C, cudaStream_t st) {
-  SFM_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2: C%%4, H%%2, W%%2 required (H=%d W=%d C=%d)", H, W, C);
+  SFM_REQUIRE(C % 4 == 0, "maxpool2: C%%4 required (C=%d)", C);   // odd H / W: the last row / column is dropped (floor)
   long long total = (long long)n_img * (H / 2) * (W / 2) * (C / 4);
   if (total == 0) return SFM_OK;
   maxpool2_kernel<<<cdiv(total, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(in),

@@ -803,6 +803,26 @@ __global__ void __launch_bounds__(256) pack_tables_kernel(const uint2* __restric
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
+// Exhaustive pair schedule on the device (matcher.py:143-144: `itertools.combinations(ids, 2)`): entry q of the
+// lexicographic list of (i < j) over n images, for q in [first, first + count) -- a rank of the multi-GPU partition
+// writes exactly its own range.  Row i starts at offset i (2n - i - 1) / 2; i comes from the closed form in double
+// precision, corrected by at most one step.
+__global__ void __launch_bounds__(256) pair_list_kernel(int n, long long first, long long count, int* __restrict__ idx0,
+                                                        int* __restrict__ idx1) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const long long q = first + k;
+  const double b = 2.0 * n - 1.0;
+  long long i = (long long)floor((b - sqrt(b * b - 8.0 * (double)q)) * 0.5);
+  if (i < 0) i = 0;
+  if (i > n - 2) i = n - 2;
+  auto row_start = [n](long long r) { return r * (2ll * n - r - 1) / 2; };
+  while (i > 0 && row_start(i) > q) i--;
+  while (i < n - 2 && row_start(i + 1) <= q) i++;
+  idx0[k] = (int)i;
+  idx1[k] = (int)(q - row_start(i) + i + 1);
+}
+
 // SimpleMatcher: S <- -sqrt(2 - 2 clamp(S, -1, 1))   (simple_matcher.py:89-90; negated so argmax == argmin)
 __global__ void neg_l2_kernel(float* __restrict__ S, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1105,6 +1125,13 @@ int pack_tables(const unsigned* tables, int n_pairs, int kcap, const int* length
   if (n_pairs == 0) return SFM_OK;
   pack_tables_kernel<<<n_pairs, 256, 0, st>>>(reinterpret_cast<const uint2*>(tables), kcap, lengths, offsets,
                                               reinterpret_cast<uint2*>(out));
+  SFM_LAUNCH_CHECK();
+  return SFM_OK;
+}
+
+int pair_list_range(int n, long long first, long long count, int* idx0, int* idx1, cudaStream_t st) {
+  if (count == 0) return SFM_OK;
+  pair_list_kernel<<<cdiv(count, 256), 256, 0, st>>>(n, first, count, idx0, idx1);
   SFM_LAUNCH_CHECK();
   return SFM_OK;
 }

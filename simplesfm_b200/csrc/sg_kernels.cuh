@@ -72,6 +72,8 @@ int sparse_depth_project(const double* xyz, const int* entry_cam, const int* ent
                          const double* extrinsics, const double* intrinsics, int n_cams, int W, int H, double* depth,
                          double* bounds, long long* winner_ws, int* error_flag, cudaStream_t st);
 
+// lexicographic (i < j) pairs [first, first + count) of n images as two int32 index arrays
+int pair_list_range(int n, long long first, long long count, int* idx0, int* idx1, cudaStream_t st);
 // (L,2) uint32 match-table compaction per pair: rows [i, matches0[i]] for matches0[i] > -1
 int compact_matches(const long long* matches0, int B, int N, unsigned* tables, int* lengths, cudaStream_t st);
 // flatten per-pair (kcap, 2) tables into one (sum lengths, 2) array; offsets = exclusive prefix sum of lengths

@@ -117,9 +117,15 @@ int detect_bf16(sfm_ctx* h, const float* images, int n, int H, int W, const unsi
 int sp_forward_detect(sfm_ctx* h, const float* images, int n, int H, int W, const unsigned char* mask, float thr,
                       int nms_radius, int border, int precision, int* cand_counts, void* ws, size_t ws_bytes,
                       bool dry, size_t* need, cudaStream_t st) {
-  SFM_REQUIRE(n >= 0 && H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0,
-              "superpoint: H and W must be positive multiples of 8 (H=%d W=%d)", H, W);
   SFM_REQUIRE(precision == 0 || precision == 1, "superpoint: unknown precision %d", precision);
+  SFM_REQUIRE(n >= 0 && H >= 8 && W >= 8, "superpoint: H and W must be at least 8 (H=%d W=%d)", H, W);
+  // Sides that are not multiples of 8 (fp32 path): like the reference, the convolutions run at the full size, every
+  // pool floors, and everything after the detector head lives on the (H/8*8, W/8*8) score map (superpoint.py:112-130).
+  // A mask has the image's shape and cannot broadcast against that map (the reference raises, superpoint.py:134).
+  SFM_REQUIRE((H % 8 == 0 && W % 8 == 0) || precision == 0,
+              "superpoint: the bf16 path needs H and W to be multiples of 8 (H=%d W=%d)", H, W);
+  SFM_REQUIRE((H % 8 == 0 && W % 8 == 0) || mask == nullptr,
+              "superpoint: a mask of size (%d, %d) does not match the (%d, %d) score map", H, W, H / 8 * 8, W / 8 * 8);
   Arena a(dry ? nullptr : ws, dry ? 0 : ws_bytes);
   SpBuffers b;
   carve(a, n, H, W, precision, b);
@@ -133,29 +139,29 @@ int sp_forward_detect(sfm_ctx* h, const float* images, int n, int H, int W, cons
   if (n == 0) return SFM_OK;
   const SpConv* c = h->sp.conv;
   if (precision == 1) return detect_bf16(h, images, n, H, W, mask, thr, nms_radius, border, cand_counts, b, st);
-  // encoder (superpoint.py:112-122)
+  // encoder (superpoint.py:112-122); H2 = H / 2 ... are the floored sizes nn.MaxPool2d(2, 2) produces
+  const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2, hh = H4 / 2, ww = W4 / 2, Hs = hh * 8, Ws = ww * 8;
   SFM_TRY(conv1a_f32(images, c[0].w, c[0].b, b.A, nullptr, n, H, W, st));
   SFM_TRY(conv(c[1], b.A, b.Bf, n, H, W, true, st));
   SFM_TRY(maxpool2_nhwc_f32(b.Bf, b.A, n, H, W, 64, st));
-  SFM_TRY(conv(c[2], b.A, b.Bf, n, H / 2, W / 2, true, st));
-  SFM_TRY(conv(c[3], b.Bf, b.A, n, H / 2, W / 2, true, st));
-  SFM_TRY(maxpool2_nhwc_f32(b.A, b.Bf, n, H / 2, W / 2, 64, st));
-  SFM_TRY(conv(c[4], b.Bf, b.A, n, H / 4, W / 4, true, st));
-  SFM_TRY(conv(c[5], b.A, b.Bf, n, H / 4, W / 4, true, st));
-  SFM_TRY(maxpool2_nhwc_f32(b.Bf, b.A, n, H / 4, W / 4, 128, st));
-  const int hh = H / 8, ww = W / 8;
+  SFM_TRY(conv(c[2], b.A, b.Bf, n, H2, W2, true, st));
+  SFM_TRY(conv(c[3], b.Bf, b.A, n, H2, W2, true, st));
+  SFM_TRY(maxpool2_nhwc_f32(b.A, b.Bf, n, H2, W2, 64, st));
+  SFM_TRY(conv(c[4], b.Bf, b.A, n, H4, W4, true, st));
+  SFM_TRY(conv(c[5], b.A, b.Bf, n, H4, W4, true, st));
+  SFM_TRY(maxpool2_nhwc_f32(b.Bf, b.A, n, H4, W4, 128, st));
   SFM_TRY(conv(c[6], b.A, b.Bf, n, hh, ww, true, st));
   SFM_TRY(conv(c[7], b.Bf, b.feat, n, hh, ww, true, st));
   // detector head (superpoint.py:125-131)
   SFM_TRY(conv(c[8], b.feat, b.A, n, hh, ww, true, st));
   SFM_TRY(conv(c[9], b.A, b.logits, n, hh, ww, false, st));
   SFM_TRY(sp_softmax_shuffle(b.logits, 65, b.smap, n, hh, ww, st));
-  SFM_TRY(sp_nms(b.smap, b.nms, n, H, W, nms_radius, st));
+  SFM_TRY(sp_nms(b.smap, b.nms, n, Hs, Ws, nms_radius, st));
   // descriptor head (superpoint.py:157-158); per-cell L2 normalisation is fused into sampling
   SFM_TRY(conv(c[10], b.feat, b.A, n, hh, ww, true, st));
   SFM_TRY(conv(c[11], b.A, b.dmap, n, hh, ww, false, st));
   // mask / threshold / border (superpoint.py:133-145)
-  SFM_TRY(sp_select(b.nms, mask, n, H, W, thr, border, b.block_tmp, b.cap, b.cand_pix, b.cand_score, b.cand_counts,
+  SFM_TRY(sp_select(b.nms, mask, n, Hs, Ws, thr, border, b.block_tmp, b.cap, b.cand_pix, b.cand_score, b.cand_counts,
                     st));
   if (cand_counts)
     SFM_CUDA(cudaMemcpyAsync(cand_counts, b.cand_counts, n * sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -177,8 +183,8 @@ int sp_forward_describe(sfm_ctx* h, int n, int H, int W, int max_kp, int align_c
     return SFM_ERR_WORKSPACE;
   }
   if (n == 0) return SFM_OK;
-  SFM_TRY(sp_rank_sort(b.cand_pix, b.cand_score, b.cand_counts, n, b.cap, max_kp, W, kp_cap, kpts_xy, scores, counts,
-                       st));
+  SFM_TRY(sp_rank_sort(b.cand_pix, b.cand_score, b.cand_counts, n, b.cap, max_kp, W / 8 * 8, kp_cap, kpts_xy, scores,
+                       counts, st));   // pixel indices are positions on the (H/8*8, W/8*8) score map
   return sp_sample_descriptors(b.dmap, n, H / 8, W / 8, kpts_xy, counts, kp_cap, align_corners, desc, kp_cap, st);
 }
 
@@ -190,7 +196,7 @@ int sp_tap(int n, int H, int W, int precision, int which, void* ws, size_t ws_by
     set_error("superpoint tap: workspace too small");
     return SFM_ERR_WORKSPACE;
   }
-  const size_t full = (size_t)n * H * W, cells = (size_t)n * (H / 8) * (W / 8);
+  const size_t full = (size_t)n * (H / 8 * 8) * (W / 8 * 8), cells = (size_t)n * (H / 8) * (W / 8);
   switch (which) {
     case 0: *out = b.feat; *cnt = cells * 128; break;
     case 1: *out = b.logits; *cnt = cells * 65; break;

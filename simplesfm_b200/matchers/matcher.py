@@ -151,9 +151,12 @@ class Matcher(object):
         """
         return self._super_glue_tables(frames, match_list, super_chunk).to_dict()
 
-    def _super_glue_tables(self, frames: List[Frame], match_list: np.ndarray, super_chunk: int = 2048):
+    def _super_glue_tables(self, frames: List[Frame], match_list: np.ndarray, super_chunk: int = 2048,
+                           exhaustive_first: int = None):
         """The hot loop (matcher.py:60-113) with compact output: `distributed.CompactTables` (pairs, per-pair
-        lengths, all rows concatenated) -- no per-pair host object until `to_dict()`."""
+        lengths, all rows concatenated) -- no per-pair host object until `to_dict()`.  `exhaustive_first`: the
+        pairs are entries [first, first + P) of the unfiltered lexicographic schedule of ids 1..n, so the index
+        arrays are generated on the device (`sfm_pair_list`) instead of being uploaded."""
         from ..distributed import CompactTables, concat_tables
         match_list = np.asarray(match_list, dtype=np.int64).reshape(-1, 2)
         if len(match_list) == 0:
@@ -162,11 +165,18 @@ class Matcher(object):
         dev = sg.device
         store = getattr(frames, 'store', None) or FeatureStore(frames, dev)
         pairs0 = np.ascontiguousarray(match_list - 1)
-        idx0_all = torch.from_numpy(np.ascontiguousarray(pairs0[:, 0]).astype(np.int32)).to(dev)
-        idx1_all = torch.from_numpy(np.ascontiguousarray(pairs0[:, 1]).astype(np.int32)).to(dev)
-        bs = int(self.super_glue_batch)
         P = len(pairs0)
         L = lib()
+        if exhaustive_first is not None:
+            idx0_all = torch.empty(P, dtype=torch.int32, device=dev)
+            idx1_all = torch.empty(P, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                check(L.sfm_pair_list(len(frames), int(exhaustive_first), P, ptr(idx0_all), ptr(idx1_all),
+                                      stream_ptr(dev)))
+        else:
+            idx0_all = torch.from_numpy(np.ascontiguousarray(pairs0[:, 0]).astype(np.int32)).to(dev)
+            idx1_all = torch.from_numpy(np.ascontiguousarray(pairs0[:, 1]).astype(np.int32)).to(dev)
+        bs = int(self.super_glue_batch)
         counts = np.asarray(store.counts, dtype=np.int64)
         uniform_hw = len(set(store.hw)) == 1
         super_chunk = max(bs, super_chunk // bs * bs)
@@ -280,14 +290,17 @@ class Matcher(object):
         from ..distributed import active_group
         return active_group(self.shard_pairs, self.process_group)
 
-    def _shard(self, match_list: np.ndarray) -> np.ndarray:
-        """Contiguous, chunk-aligned slice of the pair list for this rank (SURVEY.md 8e phase 3).
-        Chunk alignment keeps train-mode BatchNorm statistics identical to a single-GPU run."""
+    def _shard_bounds(self, n_pairs: int) -> Tuple[int, int]:
+        """[lo, hi) of this rank in a pair list of `n_pairs` entries: contiguous and chunk-aligned (SURVEY.md 8e
+        phase 3), which keeps train-mode BatchNorm statistics identical to a single-GPU run."""
         group, rank, world = self._group()
         if group is None:
-            return match_list
+            return 0, n_pairs
         from ..distributed import shard_range
-        lo, hi = shard_range(len(match_list), getattr(self, 'super_glue_batch', 1), rank, world)
+        return shard_range(n_pairs, getattr(self, 'super_glue_batch', 1), rank, world)
+
+    def _shard(self, match_list: np.ndarray) -> np.ndarray:
+        lo, hi = self._shard_bounds(len(match_list))
         return match_list[lo:hi]
 
     @staticmethod
@@ -297,8 +310,8 @@ class Matcher(object):
         pairs): the upper triangle comes from `np.triu_indices`, and a filter written with array
         arithmetic -- e.g. the reference's `lambda x: np.abs(x[0] - x[1]) < radius`
         (scripts/generate_simple_sfm_dataset_from_scene.py:140-143) -- is evaluated once on all pairs; its answer is
-        used only if it is a boolean vector that agrees with pair-by-pair evaluation on a sample, otherwise the
-        filter is applied pair by pair like the reference does."""
+        used only if it is a boolean vector that agrees with pair-by-pair evaluation (all pairs up to 20 000,
+        a 2 048-pair sample beyond), otherwise the filter is applied pair by pair like the reference does."""
         ids = np.asarray(list(ids))
         a, b = np.triu_indices(len(ids), k=1)
         every = np.stack([ids[a], ids[b]], axis=1).reshape(-1, 2)
@@ -308,7 +321,17 @@ class Matcher(object):
         try:
             ans = match_pairs_filter(every.T)
             if isinstance(ans, np.ndarray) and ans.dtype == np.bool_ and ans.shape == (len(every),):
-                probe = np.unique(np.linspace(0, len(every) - 1, num=min(len(every), 32)).astype(np.int64))
+                # The array answer is trusted only after comparison with pair-by-pair calls: EVERY pair up to 20 000
+                # pairs; beyond that 2 048 pairs (evenly spaced + seeded random), unless the filter declares itself
+                # element-wise with an attribute `vectorized = True`.
+                if getattr(match_pairs_filter, 'vectorized', False):
+                    probe = np.zeros(0, np.int64)
+                elif len(every) <= 20000:
+                    probe = np.arange(len(every))
+                else:
+                    probe = np.unique(np.concatenate([
+                        np.linspace(0, len(every) - 1, num=1024).astype(np.int64),
+                        np.random.RandomState(0).randint(0, len(every), size=1024)]))
                 if all(bool(match_pairs_filter(every[i])) == bool(ans[i]) for i in probe):
                     keep = ans
         except Exception:       # not an array-style filter
@@ -338,9 +361,13 @@ class Matcher(object):
             from ..distributed import assert_same_everywhere
             assert_same_everywhere([len(frames), len(wanted), sum(int(f.keypoints_poses.shape[0]) for f in frames)],
                                    self.device, group, what="frames / pair list")
-        mine = self._shard(wanted)
+        lo, hi = self._shard_bounds(len(wanted))
+        mine = wanted[lo:hi]
+        # unfiltered schedule over ids 1..n: the pair index arrays are generated on the device (8f-3)
+        ids = list(images_names.keys())
+        exhaustive = match_pairs_filter is None and len(ids) == len(frames) and ids == list(range(1, len(ids) + 1))
         if self.matcher_type == 'super_glue':
-            tables = self._super_glue_tables(frames, mine)
+            tables = self._super_glue_tables(frames, mine, exhaustive_first=lo if exhaustive else None)
         elif self.matcher_type == 'simple':
             tables = self._simple_tables(frames, mine)
         else:

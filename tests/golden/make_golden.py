@@ -100,6 +100,28 @@ def golden_superpoint():
         torch_version=np.array(torch.__version__))
 
 
+def golden_superpoint_odd():
+    """Image sides that are not multiples of 8 (the reference accepts them when no mask is given: the convolutions
+    run at the full size, the pools floor, keypoints come from the (h*8, w*8) score map; superpoint.py:112-171)."""
+    wpath = S.save_state_dict(S.superpoint_state_dict(0), os.path.join(TMP, "sp.pth"))
+    for tag, (H, W), mk in (("77x133", (77, 133), -1), ("101x90_top150", (101, 90), 150)):
+        img = S.textured_image(7, H + 3, W + 3)[:, :, :H, :W].contiguous()
+        m = RSP.SuperPoint(wpath, nms_radius=4, keypoint_threshold=0.005, max_keypoints=mk)
+        with torch.no_grad():
+            x = img
+            for a, b, pool in (("conv1a", "conv1b", True), ("conv2a", "conv2b", True),
+                               ("conv3a", "conv3b", True), ("conv4a", "conv4b", False)):
+                x = m.relu(getattr(m, b)(m.relu(getattr(m, a)(x))))
+                if pool:
+                    x = m.pool(x)
+            sc = torch.nn.functional.softmax(m.convPb(m.relu(m.convPa(x))), 1)[:, :-1]
+            b_, _, h, w = sc.shape
+            sc = sc.permute(0, 2, 3, 1).reshape(b_, h, w, 8, 8).permute(0, 1, 3, 2, 4).reshape(b_, h * 8, w * 8)
+            out = m({"image": img})
+        npz(f"sp_odd_{tag}", image=img, feat=x, score_map=sc, keypoints=out["keypoints"], scores=out["scores"],
+            descriptors=out["descriptors"])
+
+
 def sg_inputs(B, K0, K1, seed):
     fr = S.feature_scene(2 * B, max(K0, K1), seed=seed)
     return {"descriptors0": torch.stack([fr[i][0][:, :K0] for i in range(B)]),
@@ -344,6 +366,6 @@ def golden_sparse_depth():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (golden_superpoint, golden_superglue, golden_matcher, golden_module_functions, golden_sparse_depth):
+    for fn in (golden_superpoint, golden_superpoint_odd, golden_superglue, golden_matcher, golden_module_functions, golden_sparse_depth):
         if not only or fn.__name__ in only:
             fn()

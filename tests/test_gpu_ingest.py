@@ -184,3 +184,23 @@ def test_config3_miniature_images_to_colmap_db(tmp_path, sp_weights, sg_weights_
         total += len(ref)
     assert total > 20
     assert open(tmp_path / "colmap" / "match.txt").read().splitlines()[0] == "view_0.png view_1.png"
+
+
+def test_device_pair_list_equals_itertools(dev):
+    """`sfm_pair_list`: any range of the lexicographic (i < j) schedule, generated on the device,
+    equals `itertools.combinations` (matcher.py:143-144); 2 000 images = 1 999 000 pairs exercise the closed form."""
+    import itertools
+    from simplesfm_b200._lib import check, lib, ptr, stream_ptr
+    L = lib()
+    for n in (2, 3, 7, 50, 333, 2000):
+        total = n * (n - 1) // 2
+        a, b = np.triu_indices(n, k=1)
+        for first, count in ((0, total), (total // 3, total - total // 3), (total - 1, 1), (5 % total, 0)):
+            i0 = torch.full((max(count, 1),), -1, dtype=torch.int32, device=dev)
+            i1 = torch.full((max(count, 1),), -1, dtype=torch.int32, device=dev)
+            check(L.sfm_pair_list(n, first, count, ptr(i0), ptr(i1), stream_ptr(dev)))
+            assert np.array_equal(i0.cpu().numpy()[:count], a[first:first + count])
+            assert np.array_equal(i1.cpu().numpy()[:count], b[first:first + count])
+    assert list(zip(*np.triu_indices(7, k=1))) == list(itertools.combinations(range(7), 2))
+    with pytest.raises(Exception):
+        check(L.sfm_pair_list(5, 8, 5, ptr(i0), ptr(i1), stream_ptr(dev)))

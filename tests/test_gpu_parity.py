@@ -110,6 +110,22 @@ def test_superpoint_forward(sp, dev, tag, mk, masked):
     assert np.all(np.diff(s) <= 0)                        # sorted by score descending
 
 
+@pytest.mark.parametrize("tag,mk", [("77x133", -1), ("101x90_top150", 150)])
+def test_superpoint_sizes_not_multiple_of_8(sp, dev, tag, mk):
+    """Image sides that are not multiples of 8: the reference runs the convolutions at the full
+    size, floors in every pool and takes keypoints from the (h*8, w*8) score map (superpoint.py:112-130)."""
+    g = load_golden(f"sp_odd_{tag}")
+    m = sp(max_keypoints=mk)
+    img = t(g["image"]).to(dev)
+    out = m({"image": img})
+    rk, rs, ro = canon_keypoints(g["keypoints"], g["scores"])
+    ok, os_, oo = canon_keypoints(out["keypoints"].cpu().numpy(), out["scores"].cpu().numpy())
+    assert rk.shape == ok.shape and len(rk) > 100
+    assert np.array_equal(rk, ok)                         # keypoint indices bit-exact
+    close(os_, rs, 1e-4, 0)
+    close(out["descriptors"].cpu().numpy()[:, oo], g["descriptors"][:, ro], 1e-4, 1e-5)
+
+
 def test_superpoint_480x640(sp, dev):
     from simplesfm_b200 import synthetic
     g = load_golden("sp_480x640_top1024")
@@ -139,8 +155,12 @@ def test_superpoint_errors(sp_weights, dev):
     m = SuperPoint(sp_weights, device=dev)
     with pytest.raises(SfmError):
         m({"image": torch.zeros(1, 1, 64, 64)})           # CPU tensor: no CPU fallback
+    with pytest.raises(SfmError):                          # a mask cannot broadcast against the (56, 64) score map
+        m({"image": torch.zeros(1, 1, 60, 64, device=dev), "mask": torch.ones(1, 1, 60, 64, dtype=torch.bool, device=dev)})
+    with pytest.raises(SfmError):                          # the tcgen05 path keeps the multiple-of-8 restriction
+        SuperPoint(sp_weights, device=dev, precision="bf16")({"image": torch.zeros(1, 1, 60, 64, device=dev)})
     with pytest.raises(SfmError):
-        m({"image": torch.zeros(1, 1, 60, 64, device=dev)})   # H not a multiple of 8
+        m({"image": torch.zeros(1, 1, 7, 64, device=dev)})
     # an image with no detections returns empty tensors
     out = SuperPoint(sp_weights, device=dev, keypoint_threshold=2.0)({"image": torch.zeros(1, 1, 64, 64, device=dev)})
     assert out["keypoints"].shape == (0, 2) and out["descriptors"].shape == (256, 0)

@@ -239,3 +239,16 @@ def test_pair_list_matches_itertools_and_vectorised_filters():
     tricky = lambda x: (np.asarray(x[0]) > 0) if np.ndim(x[0]) else (x[0] % 2 == 0)
     ref = np.array([p for p in itertools.combinations(ids, 2) if tricky(np.array(p))]).reshape(-1, 2)
     assert np.array_equal(Matcher.pair_list(ids, tricky), ref)
+    # a filter with a GLOBAL reduction: its array form differs from its per-pair form on pairs a
+    # small sample would miss; up to 20 000 pairs every pair is compared, so the per-pair answer wins
+    glob = lambda x: np.abs(x[0] - x[1]) < (np.max(x[0]) if np.ndim(x[0]) else 1000) - 36
+    ref = np.array([p for p in itertools.combinations(ids, 2) if glob(np.array(p))]).reshape(-1, 2)
+    assert np.array_equal(Matcher.pair_list(ids, glob), ref)
+    # a filter that declares itself element-wise is evaluated once and not re-checked
+    calls = []
+    def banded(x):
+        calls.append(np.ndim(x[0]))
+        return np.abs(x[0] - x[1]) < 3
+    banded.vectorized = True
+    got = Matcher.pair_list(ids, banded)
+    assert calls == [1] and len(got) == sum(1 for a, b in itertools.combinations(range(40), 2) if b - a < 3)
