@@ -389,7 +389,7 @@ def run_ours(a):
     achieved = att_flop_total / (att_total_ms * 1e-3) / 1e12 if att_total_ms > 0 else 0.0
     flop_group = att_flop_total / att_groups
     traffic, traffic_src = None, None
-    for name in ("r2_attention_traffic.json", "r1_attention_traffic.json"):
+    for name in ("r2f_attention_traffic.json", "r2_attention_traffic.json", "r1_attention_traffic.json"):
         tpath = os.path.join(ROOT, "profiles", name)
         if os.path.exists(tpath):
             tj = json.load(open(tpath))

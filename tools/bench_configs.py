@@ -172,6 +172,35 @@ def config4(dev, precision, rank, world, kp=4096, n_img=19):
             "matches": int(sum(len(v) for v in table.values()))}
 
 
+def eval_mode(dev, precision, kp=2048, n_img=30):
+    """The headline workload with `bn_mode='eval'` (running statistics folded into the weights; what the reference
+    computes after `.eval()`): BatchNorm no longer couples the pairs of a chunk, so the keypoint encoder and GNN
+    layer 0 run once per image (layer-0 hoisting) instead of once per pair."""
+    from simplesfm_b200 import synthetic
+    from simplesfm_b200.matchers import Matcher
+    from simplesfm_b200.matchers.matcher import Frame
+    spw, sgw = synthetic.superpoint_state_dict(0), synthetic.superglue_state_dict(0, "indoor")
+    img = torch.zeros(1, 480, 640, device=dev)
+    frames = [Frame(d.to(dev), k.to(dev), s.to(dev), img) for d, k, s in synthetic.feature_scene(n_img, kp, seed=3)]
+    names = {i + 1: str(i) for i in range(n_img)}
+    n_pairs = n_img * (n_img - 1) // 2
+    out = {"what": f"{n_img}-image scene ({n_pairs} pairs), {kp} keypoints, indoor layout, batch 5, 20 iterations, "
+                   f"SuperGlue {precision}: train-mode BatchNorm (the reference's behaviour) vs eval-mode BatchNorm "
+                   f"with layer-0 hoisting"}
+    for mode in ("train", "eval"):
+        m = Matcher(spw, 4, 0.005, matcher_type="super_glue", super_glue_weights_path=sgw, match_threshold=0.4,
+                    sinkhorn_iterations=20, super_glue_batch=5, precision=precision, device=dev, fuse_chunks=32,
+                    bn_mode=mode)
+        run = lambda: m.match_frames(frames, names, None)[1]
+        run()
+        ms, table = _sync_ms(run, dev, reps=2)
+        out[f"pairs_per_s_{mode}"] = n_pairs / ms * 1e3
+        out[f"matches_{mode}"] = int(sum(len(v) for v in table.values()))
+        del m
+        torch.cuda.empty_cache()
+    return out
+
+
 def config5(dev, rank, world, peaks, N=4096, iters=100, total=256):
     from simplesfm_b200 import _lib
     L = _lib.lib()
@@ -220,7 +249,8 @@ def run(a, dev, rank, world, peaks):
     steps = [("config4", lambda: config4(dev, a.precision, rank, world)),
              ("config5", lambda: config5(dev, rank, world, peaks))]
     if world == 1:
-        steps = [("config1", lambda: config1(dev)), ("config3", lambda: config3(dev, a.precision))] + steps
+        steps = [("config1", lambda: config1(dev)), ("config3", lambda: config3(dev, a.precision)),
+                 ("eval_mode", lambda: eval_mode(dev, a.precision))] + steps
     for name, fn in steps:
         t0 = time.perf_counter()
         try:
