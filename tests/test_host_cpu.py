@@ -52,7 +52,9 @@ def test_workspace_queries_are_shape_functions():
     assert L.sfm_superglue_workspace_bytes(5, 0, 10, 0, 1) == 0               # invalid shape -> 0 + error text
     assert b"K0, K1 > 0" in L.sfm_last_error()
     assert L.sfm_superpoint_workspace_bytes(1, 480, 640, 0) > 2 * 480 * 640 * 64 * 4
-    assert L.sfm_superpoint_workspace_bytes(1, 481, 640, 0) == 0
+    assert L.sfm_superpoint_workspace_bytes(1, 481, 640, 0) > 0               # fp32 path: any size >= 8, like the reference
+    assert L.sfm_superpoint_workspace_bytes(1, 481, 640, 1) == 0              # tcgen05 path: multiples of 8
+    assert L.sfm_superpoint_workspace_bytes(1, 7, 640, 0) == 0
     assert L.sfm_sinkhorn_workspace_bytes(2, 100, 90) > 0
 
 
