@@ -5,6 +5,7 @@
 //   top-k + descending sort with a fixed tie rule  (superpoint.py:35-39,148-151,165-171)
 //   bilinear descriptor sampling + double L2 normalisation (superpoint.py:42-54,157-163)
 #include "sp_post.cuh"
+#include <algorithm>
 
 namespace sfm {
 
@@ -297,6 +298,7 @@ __device__ __forceinline__ unsigned f2ord(float f) {
 // 64 candidates per block (a few thousand candidates per image must still fill 148 SMs); the keys of all
 // candidates stream through a 256-entry shared tile that every thread scans four at a time.
 constexpr int RANK_THREADS = 64;
+constexpr int SORT_MAX = 8192;   // candidates one CTA sorts in shared memory (64 KB of keys)
 __global__ void __launch_bounds__(RANK_THREADS) rank_sort_kernel(const int* __restrict__ cand_pix,
                                                                 const float* __restrict__ cand_score,
                                                                 const int* __restrict__ counts, int cap, int max_kp,
@@ -305,15 +307,16 @@ __global__ void __launch_bounds__(RANK_THREADS) rank_sort_kernel(const int* __re
                                                                 int* __restrict__ out_counts) {
   int img = blockIdx.y;
   int C = min(counts[img], cap);
+  if (C <= SORT_MAX) return;   // sorted by bitonic_rank_kernel
   int keep = (max_kp >= 0 && max_kp < C) ? max_kp : C;
   keep = min(keep, out_cap);
   if (blockIdx.x == 0 && threadIdx.x == 0) out_counts[img] = keep;
-  int i = blockIdx.x * RANK_THREADS + threadIdx.x;
-  if (blockIdx.x * RANK_THREADS >= C) return;
   const float* sc = cand_score + (long long)img * cap;
   const int* px = cand_pix + (long long)img * cap;
-  unsigned ki = i < C ? f2ord(sc[i]) : 0u;
   __shared__ __align__(16) unsigned tile[256];
+  for (int blk = blockIdx.x; blk * RANK_THREADS < C; blk += gridDim.x) {   // block-uniform
+  int i = blk * RANK_THREADS + threadIdx.x;
+  unsigned ki = i < C ? f2ord(sc[i]) : 0u;
   int rank = 0;
   for (int base = 0; base < C; base += 256) {
 #pragma unroll
@@ -339,6 +342,57 @@ __global__ void __launch_bounds__(RANK_THREADS) rank_sort_kernel(const int* __re
     kpts_xy[((long long)img * out_cap + rank) * 2 + 0] = (float)x;
     kpts_xy[((long long)img * out_cap + rank) * 2 + 1] = (float)y;
     scores_out[(long long)img * out_cap + rank] = sc[i];
+  }
+  }
+}
+
+// The usual case (a few thousand candidates per image): one CTA per image sorts 64-bit keys
+// (inverted ordered score | candidate index) with a bitonic network in shared memory -- ascending keys are
+// (score descending, pixel ascending), the same total order as the rank counting above -- and writes the first
+// `keep` entries.  O(C log^2 C) instead of O(C^2): 4 700 candidates take ~5 us instead of ~25.
+__global__ void __launch_bounds__(1024) bitonic_rank_kernel(const int* __restrict__ cand_pix,
+                                                            const float* __restrict__ cand_score,
+                                                            const int* __restrict__ counts, int cap, int max_kp, int W,
+                                                            int out_cap, float* __restrict__ kpts_xy,
+                                                            float* __restrict__ scores_out,
+                                                            int* __restrict__ out_counts) {
+  extern __shared__ __align__(16) unsigned long long keys[];
+  const int img = blockIdx.x;
+  const int C = min(counts[img], cap);
+  if (C > SORT_MAX) return;    // rank_sort_kernel takes this image
+  int keep = (max_kp >= 0 && max_kp < C) ? max_kp : C;
+  keep = min(keep, out_cap);
+  if (threadIdx.x == 0) out_counts[img] = keep;
+  if (keep == 0) return;
+  const float* sc = cand_score + (long long)img * cap;
+  const int* px = cand_pix + (long long)img * cap;
+  int n2 = 64;
+  while (n2 < C) n2 <<= 1;
+  for (int i = threadIdx.x; i < n2; i += 1024)
+    keys[i] = i < C ? ((unsigned long long)(~f2ord(sc[i])) << 32) | (unsigned)i : ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int q = threadIdx.x; q < (n2 >> 1); q += 1024) {
+        const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1));   // the lower index of compare-exchange q
+        const int l = i | j;
+        const unsigned long long a = keys[i], b = keys[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) {
+          keys[i] = b;
+          keys[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int r = threadIdx.x; r < keep; r += 1024) {
+    const int i = (int)(keys[r] & 0xffffffffu);
+    const int p = px[i];
+    const int y = p / W, x = p - y * W;
+    kpts_xy[((long long)img * out_cap + r) * 2 + 0] = (float)x;
+    kpts_xy[((long long)img * out_cap + r) * 2 + 1] = (float)y;
+    scores_out[(long long)img * out_cap + r] = sc[i];
   }
 }
 
@@ -460,10 +514,15 @@ int sp_select(const float* nms, const unsigned char* mask, int n_img, int H, int
 int sp_rank_sort(const int* cand_pix, const float* cand_score, const int* counts, int n_img, int cap, int max_kp,
                  int W, int out_cap, float* kpts_xy, float* scores_out, int* out_counts, cudaStream_t st) {
   if (n_img == 0) return SFM_OK;
-  dim3 grid(cdiv(cap, RANK_THREADS), n_img);
+  const size_t smem = sizeof(unsigned long long) * SORT_MAX;
+  SFM_SMEM_OPT_IN(bitonic_rank_kernel, smem);
+  bitonic_rank_kernel<<<n_img, 1024, smem, st>>>(cand_pix, cand_score, counts, cap, max_kp, W, out_cap, kpts_xy,
+                                                 scores_out, out_counts);
+  // images with more than SORT_MAX candidates (every block returns at once otherwise)
+  dim3 grid(std::min(cdiv(cap, RANK_THREADS), 592), n_img);
   rank_sort_kernel<<<grid, RANK_THREADS, 0, st>>>(cand_pix, cand_score, counts, cap, max_kp, W, out_cap, kpts_xy, scores_out,
                                          out_counts);
-  SFM_LAUNCH_CHECK();
+  SFM_LAUNCH_CHECK_N(2);
   return SFM_OK;
 }
 

@@ -126,6 +126,35 @@ def test_superpoint_sizes_not_multiple_of_8(sp, dev, tag, mk):
     close(out["descriptors"].cpu().numpy()[:, oo], g["descriptors"][:, ro], 1e-4, 1e-5)
 
 
+@pytest.mark.parametrize("radius,thr,mk", [(1, 0.0, 1500), (4, 0.0, -1), (2, 0.0, 3000)])
+def test_superpoint_rank_sort_paths_vs_oracle(sp, sp_weights, dev, radius, thr, mk):
+    """Candidate counts on both sides of the 8 192-key limit of the shared-memory bitonic sort (nms_radius 1 at
+    threshold 0 leaves > 20 000 candidates -> rank-counting kernel; radius 4 stays below -> bitonic kernel): the
+    kept keypoints, their order (score descending, pixel ascending on ties) and scores equal the oracle's."""
+    import sfm_oracle as O
+    from simplesfm_b200 import synthetic
+    img = synthetic.textured_image(2, 240, 320)
+    out = sp(nms_radius=radius, keypoint_threshold=thr, max_keypoints=mk)({"image": img.to(dev)})
+    ref = O.superpoint_forward(sp_weights, img, None, radius, thr, mk, 4)
+    kp, sc = out["keypoints"].cpu().numpy(), out["scores"].cpu().numpy()
+    got = {(int(x), int(y)): float(v) for (x, y), v in zip(kp, sc)}
+    want = {(int(x), int(y)): float(v) for (x, y), v in zip(ref["keypoints"].numpy(), ref["scores"].numpy())}
+    print(f"radius {radius}: {len(got)} keypoints kept")
+    assert len(got) == len(want) == len(kp)
+    # the kept SET is the oracle's; with a top-k cut a keypoint may be exchanged only against one whose score agrees
+    # with the k-th score to float32 rounding (the GPU and CPU convolutions round differently)
+    cut = min(want.values())
+    for key in set(got) ^ set(want):
+        assert mk > 0 and abs((got.get(key) or want.get(key)) - cut) <= 2e-6 * max(cut, 1e-3), (key, cut)
+    for key in set(got) & set(want):
+        assert abs(got[key] - want[key]) <= 1e-4 * abs(want[key]) + 1e-7
+    # the order is (score descending, pixel index ascending on exact ties) in the GPU's own scores
+    pix = kp[:, 1].astype(np.int64) * 320 + kp[:, 0].astype(np.int64)
+    assert np.all(np.diff(sc) <= 0)
+    same = np.diff(sc) == 0
+    assert np.all(np.diff(pix)[same] > 0)
+
+
 def test_superpoint_480x640(sp, dev):
     from simplesfm_b200 import synthetic
     g = load_golden("sp_480x640_top1024")
