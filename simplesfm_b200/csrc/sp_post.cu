@@ -373,14 +373,26 @@ __global__ void __launch_bounds__(1024) bitonic_rank_kernel(const int* __restric
   __syncthreads();
   for (int k = 2; k <= n2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int q = threadIdx.x; q < (n2 >> 1); q += 1024) {
-        const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1));   // the lower index of compare-exchange q
-        const int l = i | j;
-        const unsigned long long a = keys[i], b = keys[l];
-        const bool up = (i & k) == 0;
-        if ((a > b) == up) {
-          keys[i] = b;
-          keys[l] = a;
+      // the compare-exchanges of a stage are independent: all loads first, then the swaps (up to 4 per thread)
+      unsigned long long a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int q = threadIdx.x + u * 1024;
+        if (q < (n2 >> 1)) {
+          const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1));   // the lower index of compare-exchange q
+          a[u] = keys[i];
+          b[u] = keys[i | j];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int q = threadIdx.x + u * 1024;
+        if (q < (n2 >> 1)) {
+          const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+          if ((a[u] > b[u]) == ((i & k) == 0)) {
+            keys[i] = b[u];
+            keys[i | j] = a[u];
+          }
         }
       }
       __syncthreads();
