@@ -60,18 +60,32 @@ __global__ void __launch_bounds__(NTHREADS) gemm_f32_kernel(GemmF32 p) {
   }
 
   float4 ra[2], rb[2];
+  // implicit 3x3 convolution: the filter tap changes every Cin / BK k-tiles, so the tap's source pixel (pointer and
+  // validity per row) is kept across k-tiles and only the channel offset advances -- the kernel is issue-bound and
+  // the per-tile address arithmetic (a division by Cin, bounds tests, 64-bit multiplies) cost a quarter of its slots
+  const float* tap_ptr[2] = {nullptr, nullptr};
+  int tap_next = 0, ci_next = 0;   // position of the NEXT load_tiles call (k0 advances by BK each call)
   auto load_tiles = [&](int k0) {
     // A
     if (MODE == 2) {
-      int tap = k0 / p.convCin;
-      int ci = k0 - tap * p.convCin + akq;
-      int ky = tap / 3 - 1, kx = tap % 3 - 1;
+      (void)k0;
+      if (ci_next == 0) {   // new tap (block-uniform)
+        const int ky = tap_next / 3 - 1, kx = tap_next - (tap_next / 3) * 3 - 1;
 #pragma unroll
-      for (int i = 0; i < 2; i++) {
-        int yy = cy[i] + ky, xx = cx[i] + kx;
-        bool ok = rvalid[i] && yy >= 0 && yy < p.convH && xx >= 0 && xx < p.convW;
-        ra[i] = ok ? *reinterpret_cast<const float4*>(A + (cbase[i] + (long long)yy * p.convW + xx) * p.convCin + ci)
-                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 2; i++) {
+          const int yy = cy[i] + ky, xx = cx[i] + kx;
+          const bool ok = rvalid[i] && yy >= 0 && yy < p.convH && xx >= 0 && xx < p.convW;
+          tap_ptr[i] = ok ? A + (cbase[i] + (long long)yy * p.convW + xx) * p.convCin + akq : nullptr;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+        ra[i] = tap_ptr[i] != nullptr ? *reinterpret_cast<const float4*>(tap_ptr[i] + ci_next)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      ci_next += BK;
+      if (ci_next >= p.convCin) {
+        ci_next = 0;
+        tap_next++;
       }
     } else {
       int k = k0 + akq;
@@ -228,7 +242,10 @@ int launch_gemm(const GemmF32& p, cudaStream_t st) {
   if (MODE == 1) SFM_REQUIRE(p.ldb % 4 == 0 && p.sB0 % 4 == 0 && p.sB1 % 4 == 0, "gemm_f32(nn): ldb/strides %% 4 != 0");
   if (p.A2) SFM_REQUIRE(p.K1 % BK == 0 && p.lda2 % 4 == 0, "gemm_f32: split point must be a multiple of %d", BK);
   if (MODE == 2) SFM_REQUIRE(p.convCin % BK == 0 && p.K == 9 * p.convCin, "conv3x3_f32: Cin must be a multiple of 16");
-  if (p.N <= 64) {
+  // 64-wide column tiles also when the 128-wide grid would leave most of the machine idle (SuperPoint's 60 x 80
+  // layers: 150 CTAs of 8 warps on 148 SMs); the accumulation order per output element does not change
+  const long long ctas128 = (long long)cdiv(p.N, 128) * cdiv(p.M, BM) * p.batch;
+  if (p.N <= 64 || ctas128 < 2 * 148) {
     dim3 grid(cdiv(p.N, 64), cdiv(p.M, BM), p.batch);
     gemm_f32_kernel<64, MODE><<<grid, NTHREADS, 0, st>>>(p);
   } else {
