@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--iters", type=int, default=20, help="sinkhorn_iterations (Matcher default 20)")
     ap.add_argument("--bn", default="train", choices=["train", "eval"])
     ap.add_argument("--cpu-pairs", type=int, default=5, help="pairs in the bounded CPU sample (one Matcher chunk)")
-    ap.add_argument("--fuse-chunks", type=int, default=32, help="Matcher chunks launched together (BN stats stay per chunk)")
+    ap.add_argument("--fuse-chunks", type=int, default=51, help="Matcher chunks launched together (BN stats stay per chunk)")
     ap.add_argument("--sp-precision", default="fp32", choices=["fp32", "bf16"], help="SuperPoint precision of e2e_images")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configs")

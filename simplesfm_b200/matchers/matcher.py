@@ -91,7 +91,7 @@ class Matcher(object):
                  precision: str = 'fp32',
                  device: str = 'cuda',
                  shard_pairs: bool = False,
-                 fuse_chunks: int = 32,
+                 fuse_chunks: int = 51,
                  superpoint_precision: str = 'fp32',
                  extract_batch: int = 8,
                  decode_threads: int = 4,
@@ -231,12 +231,23 @@ class Matcher(object):
                     h0, h1 = next(iter(hw0)), next(iter(hw1))
                 key = (k0, k1, h0, h1)
                 full = (c1 - c0) == bs
-                if (plan and full and tuple(plan[-1][2:6]) == key and plan[-1][6] < fuse_limit
-                        and plan[-1][1] == plan[-1][6] * bs):
+                if (plan and full and tuple(plan[-1][2:6]) == key and plan[-1][1] == plan[-1][6] * bs):
                     plan[-1][1] += bs
                     plan[-1][6] += 1
                 else:
                     plan.append([c0, c1 - c0, *key, 1])
+            # a run of fusable chunks longer than the limit is cut into EQUAL launches (245 chunks at a limit of 51 ->
+            # 5 x 49, not 4 x 51 + 41): every launch then fills the SMs equally well, no small tail launch
+            runs, plan = plan, []
+            for c0, B, k0, k1, h0, h1, groups in runs:
+                n_launch = -(-groups // fuse_limit)
+                base, extra = divmod(groups, n_launch)
+                for li in range(n_launch):
+                    g = base + (1 if li < extra else 0)
+                    nb = min(g * bs, B)
+                    plan.append([c0, nb, k0, k1, h0, h1, g])
+                    c0 += nb
+                    B -= nb
             for c0, B, k0, k1, hw0, hw1, groups in plan:
                 c1 = c0 + B
                 if k0 == 0 or k1 == 0:      # reference early-out: no matches (superglue.py:240-247)

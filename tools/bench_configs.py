@@ -155,7 +155,7 @@ def config4(dev, precision, rank, world, kp=4096, n_img=19):
     from simplesfm_b200.matchers.matcher import Frame
     spw, sgw = synthetic.superpoint_state_dict(0), synthetic.superglue_state_dict(1, "outdoor")
     m = Matcher(spw, 4, 0.005, matcher_type="super_glue", super_glue_weights_path=sgw, match_threshold=0.4,
-                sinkhorn_iterations=20, super_glue_batch=5, precision=precision, device=dev, fuse_chunks=32)
+                sinkhorn_iterations=20, super_glue_batch=5, precision=precision, device=dev, fuse_chunks=51)
     img = torch.zeros(1, 480, 640, device=dev)
     frames = [Frame(d.to(dev), k.to(dev), s.to(dev), img) for d, k, s in synthetic.feature_scene(n_img, kp, seed=5 + rank)]
     names = {i + 1: str(i) for i in range(n_img)}
@@ -189,7 +189,7 @@ def eval_mode(dev, precision, kp=2048, n_img=30):
                    f"with layer-0 hoisting"}
     for mode in ("train", "eval"):
         m = Matcher(spw, 4, 0.005, matcher_type="super_glue", super_glue_weights_path=sgw, match_threshold=0.4,
-                    sinkhorn_iterations=20, super_glue_batch=5, precision=precision, device=dev, fuse_chunks=32,
+                    sinkhorn_iterations=20, super_glue_batch=5, precision=precision, device=dev, fuse_chunks=51,
                     bn_mode=mode)
         run = lambda: m.match_frames(frames, names, None)[1]
         run()
