@@ -154,3 +154,55 @@ def test_cuda_path_edge_cases():
     # a point exactly on x == W: the reference's indexed write raises IndexError
     with pytest.raises(IndexError):
         U.sparse_depth_maps(np.array([[0.5, 0.0, 1.0]]), np.zeros(1, np.int32), np.zeros(1, np.int32), eye, intr, 8, 6)
+
+
+@pytest.mark.gpu
+def test_mixed_image_sizes_and_text_model_vs_oracle(tmp_path):
+    """Views of two different resolutions (one launch per image size) and a text-format sparse model, end to end
+    through `generate_sparse_depth_from_colmap`, against the oracle's per-camera loop."""
+    from simplesfm_b200.dataset import simple_sfm_dataset_utils as U
+    rng = np.random.RandomState(11)
+    root = tmp_path / "ds"
+    os.makedirs(root / "sparse_txt")
+    n_cam, n_pts = 5, 3000
+    frames = []
+    for i in range(n_cam):
+        a = 0.3 * (i - 2)
+        c2w = np.eye(4)
+        c2w[:3, :3] = [[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]
+        c2w[:3, 3] = [-2.4 * np.sin(a), 0.05 * i, -2.4 * np.cos(a)]
+        m = c2w.copy()
+        m[0:3, 1] *= -1
+        m[0:3, 2] *= -1
+        m = m[[1, 0, 2, 3], :]
+        W, H = ((40, 30), (56, 44))[i % 2]
+        frames.append({"id": i, "file_path": f"images/v{i}.png", "transform_matrix": m.tolist(),
+                       "intrinsic": {"f_x": 1.0, "f_y": 1.3, "c_x": 0.5, "c_y": 0.5,
+                                     "original_resolution_x": W, "original_resolution_y": H}})
+    with open(root / "views_data.json", "w") as fh:
+        json.dump({"frames": frames[::-1]}, fh)
+    lines = ["# 3D point list"]
+    for k in range(n_pts):
+        x, y, z = (float(v) for v in rng.uniform(-0.9, 0.9, 3))
+        ids = rng.randint(1, n_cam + 1, size=rng.randint(1, 4))
+        track = " ".join(f"{int(i)} {int(rng.randint(0, 9))}" for i in ids)
+        lines.append(f"{k + 1} {x!r} {y!r} {z!r} 9 9 9 {float(rng.uniform(0.1, 3.0))!r} {track}")
+    (root / "sparse_txt" / "points3D.txt").write_text("\n".join(lines) + "\n")
+    (root / "sparse_txt" / "cameras.txt").write_text("# none\n")
+    (root / "sparse_txt" / "images.txt").write_text("# none\n")
+    U.generate_sparse_depth_from_colmap(str(root), sparse_colmap_output_path=str(root / "sparse_txt"), scale=1,
+                                        error_threshold=1.5)
+    xyz, err, tp, ti = U.read_points3d_tracks(root / "sparse_txt")
+    points = [(xyz[j], float(err[j]), ti[tp == j]) for j in range(n_pts)]
+    out = json.load(open(root / "views_data.json"))
+    cams = {c[3]: c for c in O.simple_sfm_json_cameras({"frames": frames})}
+    total = 0
+    for f in out["frames"]:
+        w2c, K, size, cid, name = cams[f["id"]]
+        want, mask, _ = O.sparse_depth_for_camera(points, w2c, K, size, cid, 1, 1.5)
+        d = np.load(root / f["sparse_depth_path"], allow_pickle=True).item()
+        assert d["sparse_depth"].shape == (1, size[0], size[1])
+        assert np.array_equal(d["sparse_depth_mask"], mask)
+        np.testing.assert_allclose(d["sparse_depth"], want, rtol=1e-12, atol=1e-12)
+        total += int(mask.sum())
+    assert total > 1000
