@@ -124,10 +124,12 @@ class CompactTables(NamedTuple):
     def to_dict(self):
         """{(np.int64 id1, np.int64 id2): (L, 2) uint32} in pair order -- the reference's match table
         (matcher.py:103-109)."""
-        cuts = np.cumsum(self.lens)[:-1]
-        parts = np.split(self.rows, cuts) if len(self.lens) else []
-        a, b = self.pairs[:, 0], self.pairs[:, 1]
-        return {(a[i], b[i]): parts[i] for i in range(len(parts))}
+        # plain slices of the flat row array (views): `np.split` and per-element array indexing cost 2.5x as much,
+        # and on the database writer's rank this loop runs over the pairs of ALL ranks
+        offs = np.concatenate([[0], np.cumsum(self.lens)]).tolist()
+        rows = self.rows
+        a, b = list(self.pairs[:, 0]), list(self.pairs[:, 1])
+        return {(a[i], b[i]): rows[offs[i]:offs[i + 1]] for i in range(len(a))}
 
 
 def concat_tables(parts: Sequence[CompactTables]) -> CompactTables:
