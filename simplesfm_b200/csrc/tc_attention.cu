@@ -50,7 +50,15 @@ __device__ long long g_att_trace[TRACE_NG * 64];
 #endif
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16, 128-byte swizzled rows
 // warp 0: TMA producer; warps 1..NT: one MMA issuer per query tile; then NT softmax warpgroups
-template <int NT> struct AttCfg { static constexpr int SW0 = 1 + NT; static constexpr int THREADS = (1 + NT) * 32 + NT * 128; };
+// Softmax warpgroups first (warps 0 .. 4 NT - 1: warpgroup t = query tile t, TMEM quadrant = warp % 4), then the TMA
+// producer and the NT issuers.
+template <int NT> struct AttCfg {
+  static constexpr int SW0 = 0;
+  static constexpr int PRODUCER = 4 * NT, ISSUER0 = 4 * NT + 1;
+  static constexpr int THREADS = (1 + NT) * 32 + NT * 128;
+};
+// (`setmaxnreg` cannot move registers to the softmax warpgroups in this layout: the producer / issuer warps form a
+// partial warpgroup of three and the instruction never returns there; a 12th warp to complete it costs 8 %.)
 
 __device__ __forceinline__ void att_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -149,7 +157,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == AttCfg<NT>::PRODUCER && lane == 0) {
     tma_prefetch_desc(&map);
     tma_prefetch_desc(&map_out);
     for (int q = 0; q < 2; q++) {
@@ -168,7 +176,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<NT * 256>(&bars->tmem_base);
+  if (warp == AttCfg<NT>::ISSUER0) tmem_alloc<NT * 256>(&bars->tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -177,7 +185,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
 
   // Every barrier of the S / P / O hand-shake completes exactly once per K/V step, so one CTA-wide step
   // counter g (running across units) gives all parities; the K/V ring stage is g % KV_STAGES.
-  if (warp == 0) {
+  if (warp == AttCfg<NT>::PRODUCER) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int g = 0, it = 0;
@@ -197,14 +205,14 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
         }
       }
     }
-  } else if (warp <= NT) {
+  } else if (warp > AttCfg<NT>::PRODUCER) {
     // ------------------------------------------------------------------ MMA issuers: ONE PER QUERY TILE
     // Each tile's chain  S_t(g+1) <- s_free_t(g),  P V_t(g) <- p_full_t(g)  is driven by its own thread, so a tile
     // never waits behind a barrier of the other tile (a single in-order issuer couples the two softmax groups:
     // its four waits per step form one cycle, and whichever group runs late stalls the other's P V).  The two
     // tiles share only the K/V ring and the Q buffers, released when BOTH issuers' MMAs on them have completed
     // (kv_empty / q_empty count NT; tcgen05.commit tracks the issuing thread's own MMAs).
-    const int t = warp - 1;
+    const int t = warp - AttCfg<NT>::ISSUER0;
     // The WHOLE warp runs this loop and one elected lane issues: descriptors, TMEM addresses and barrier addresses then
     // live in uniform registers.  Under `if (lane == 0)` they are per-thread values and every tcgen05.mma is wrapped
     // in an ELECT / R2UR.BROADCAST / branch sequence (~85 clocks per MMA: the eight P V MMAs of a step took 700
@@ -434,7 +442,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap map, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<NT * 256>(tmem);
+  if (warp == AttCfg<NT>::ISSUER0) tmem_dealloc<NT * 256>(tmem);
 }
 
 // Exact recomputation of the rows the main kernel flagged (a score jump of more than 2^90 inside one K/V step; see
