@@ -204,3 +204,41 @@ def test_device_pair_list_equals_itertools(dev):
     assert list(zip(*np.triu_indices(7, k=1))) == list(itertools.combinations(range(7), 2))
     with pytest.raises(Exception):
         check(L.sfm_pair_list(5, 8, 5, ptr(i0), ptr(i1), stream_ptr(dev)))
+
+
+def test_matcher_on_image_sizes_not_multiple_of_8(tmp_path, sp_weights, sg_weights, dev):
+    """The whole path (PNG files -> batched ingestion -> SuperPoint fp32 -> SuperGlue fp32 -> tables) on 150 x 203
+    images: batched extraction equals the per-image loop, the frames equal the CPU oracle's SuperPoint on the same
+    pixels (keypoint sets bit-exact), and the match table equals the oracle's for the extracted frames."""
+    import sfm_oracle as O
+    from PIL import Image
+    from simplesfm_b200.matchers import Matcher
+    H, W = 150, 203
+    items = []
+    for i in range(3):
+        Image.fromarray(_grey_u8(40 + i, H + 2, W + 5, shift=(2 * i, i))[:H, :W]).save(tmp_path / f"odd_{i}.png")
+        items.append({"file_path": f"./odd_{i}.png"})
+    (tmp_path / "views_data.json").write_text(json.dumps({"frames": items}))
+    kw = dict(matcher_type="super_glue", super_glue_weights_path=sg_weights, match_threshold=0.2,
+              sinkhorn_iterations=10, super_glue_batch=2, max_keypoints=300, device=dev)
+    fa, ta, _ = Matcher(sp_weights, 4, 0.005, extract_batch=1, **kw).match_simple_sfm_dataset(str(tmp_path))
+    fb, tb, _ = Matcher(sp_weights, 4, 0.005, extract_batch=3, **kw).match_simple_sfm_dataset(str(tmp_path))
+    _same_frames(fa, fb)
+    _same_tables(ta, tb)
+    oframes = []
+    for i, f in enumerate(fb):
+        assert tuple(f.image.shape) == (1, H, W)
+        px = np.asarray(Image.open(tmp_path / f"odd_{i}.png")).astype(np.float32) / 255
+        ref = O.superpoint_forward(sp_weights, torch.from_numpy(px)[None, None], None, 4, 0.005, 300, 4)
+        got = {(int(x), int(y)) for x, y in f.keypoints_poses.cpu().numpy()}
+        want = {(int(x), int(y)) for x, y in ref["keypoints"].numpy()}
+        assert len(want) > 50 and got == want
+        assert max(x for x, _ in got) < W // 8 * 8 and max(y for _, y in got) < H // 8 * 8
+        oframes.append((f.descriptors.cpu(), f.keypoints_poses.cpu(), f.scores.cpu(), torch.zeros(1, H, W)))
+    otab = O.superglue_match_table(sg_weights, oframes, O.pair_list([1, 2, 3]), 2, 10, 0.2, "train")
+    assert set(otab) == set(tb)
+    n = 0
+    for k in otab:
+        assert np.array_equal(np.asarray(otab[k]), tb[k]), k
+        n += len(tb[k])
+    assert n > 0
