@@ -1,4 +1,6 @@
 #include "gemm_f32.cuh"
+#include <algorithm>
+#include <cstdint>
 
 namespace sfm {
 
@@ -312,6 +314,71 @@ __global__ void __launch_bounds__(256) conv1a_kernel(const float* __restrict__ i
   }
 }
 
+// conv1a, four pixels per thread (W % 4 == 0): thread = (8-channel group, 4 consecutive pixels of one row).  The
+// 3 x 6 input window comes from three 16-byte loads plus the two edge columns, the index arithmetic (two divisions,
+// 36 bounds tests) is paid once per four pixels, and 288 independent FMAs hide the load latency.  Per output the
+// taps are accumulated in the same (ky, kx) order as conv1a_kernel: fp32 results are bit-identical.
+__global__ void __launch_bounds__(128) conv1a_x4_kernel(const float* __restrict__ img, const float* __restrict__ w9,
+                                                        const float* __restrict__ bias, float* __restrict__ out,
+                                                        __nv_bfloat16* __restrict__ out_h, int n_img, int H, int W) {
+  const int cg = threadIdx.x & 7, lq = threadIdx.x >> 3;   // channel group, quad lane (0..15)
+  float w[8][9], b[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    b[c] = bias[cg * 8 + c];
+#pragma unroll
+    for (int t = 0; t < 9; t++) w[c][t] = w9[(cg * 8 + c) * 9 + t];
+  }
+  const int wq = W >> 2;                      // quads per row
+  const long long quads = (long long)n_img * H * wq;
+  for (long long q = (long long)blockIdx.x * 16 + lq; q < quads; q += (long long)gridDim.x * 16) {
+    const long long row = q / wq;             // image row index over the whole batch
+    const int x0 = (int)(q - row * wq) * 4;
+    const int y = (int)(row % H);
+    const float* im = img + row * W;          // start of this image row
+    float v[3][6];
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+      const int yy = y + ky - 1;
+      if (yy >= 0 && yy < H) {
+        const float* r = im + (ky - 1) * W + x0;
+        const float4 m = *reinterpret_cast<const float4*>(r);
+        v[ky][0] = x0 > 0 ? r[-1] : 0.f;
+        v[ky][1] = m.x; v[ky][2] = m.y; v[ky][3] = m.z; v[ky][4] = m.w;
+        v[ky][5] = x0 + 4 < W ? r[4] : 0.f;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++) v[ky][k] = 0.f;
+      }
+    }
+    const long long pix0 = row * W + x0;
+#pragma unroll
+    for (int px = 0; px < 4; px++) {
+      float o[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        float a = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+          for (int kx = 0; kx < 3; kx++) a = fmaf(v[ky][px + kx], w[c][ky * 3 + kx], a);
+        o[c] = fmaxf(a + b[c], 0.f);
+      }
+      if (out_h != nullptr) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]),
+                       h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
+        *reinterpret_cast<uint4*>(out_h + (pix0 + px) * 64 + cg * 8) =
+            make_uint4(*reinterpret_cast<unsigned*>(&h0), *reinterpret_cast<unsigned*>(&h1),
+                       *reinterpret_cast<unsigned*>(&h2), *reinterpret_cast<unsigned*>(&h3));
+      } else {
+        float4* dst = reinterpret_cast<float4*>(out + (pix0 + px) * 64 + cg * 8);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+    }
+  }
+}
+
 __global__ void maxpool2_kernel(const float4* __restrict__ in, float4* __restrict__ out, int n_img, int H, int W,
                                 int C4) {
   int Ho = H / 2, Wo = W / 2;
@@ -344,7 +411,13 @@ int conv1a_f32(const float* img, const float* w9, const float* bias, float* out,
                int H, int W, cudaStream_t st) {
   long long total = (long long)n_img * H * W;
   if (total == 0) return SFM_OK;
-  conv1a_kernel<<<cdiv(total, C1A_PIX_PER_BLOCK), 256, 0, st>>>(img, w9, bias, out, out_h, n_img, H, W);
+  if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0) {
+    const long long quads = total / 4;
+    const int grid = (int)std::min<long long>(cdiv(quads, 16), 148 * 16);
+    conv1a_x4_kernel<<<grid, 128, 0, st>>>(img, w9, bias, out, out_h, n_img, H, W);
+  } else {
+    conv1a_kernel<<<cdiv(total, C1A_PIX_PER_BLOCK), 256, 0, st>>>(img, w9, bias, out, out_h, n_img, H, W);
+  }
   SFM_LAUNCH_CHECK();
   return SFM_OK;
 }
