@@ -6,10 +6,11 @@
 // persistent (one per SM, units strided by the grid): the Q tiles of the next unit are loaded into a second
 // buffer and its first S = Q K^T is issued while the softmax groups still normalise / store the previous
 // unit's output, so barrier setup, TMEM allocation and the load / store latencies are paid once per CTA.
-//   warp 0     : TMA producer (Q tiles per unit, K/V tiles through a 3-stage ring that runs across units)
-//   warps 1-2  : tcgen05.mma issuers, one per query tile:  S_t = Q_t K_j^T  (SS, fp32 in TMEM),
-//                O_t = P_t V_j  (A = P from TMEM)
-//   warps 3-6  : softmax warpgroup of tile 0 (thread = query row), warps 7-10: tile 1
+//   warps 0-3  : softmax warpgroup of tile 0 (thread = query row), warps 4-7: tile 1
+//   warp 8     : TMA producer (Q tiles per unit, K/V tiles through a 3-stage ring that runs across units)
+//   warps 9-10 : tcgen05.mma issuers, one per query tile (the whole warp runs converged, one elected lane issues):
+//                S_t = Q_t K_j^T  (SS, fp32 in TMEM),  O_t = P_t V_j  (A = P from TMEM)
+// The unit's output leaves through a swizzled shared-memory staging tile and one TMA store (att_epilogue).
 // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512)
 // O accumulates in TMEM across K/V tiles.  The softmax threads exponentiate a step relative to the row maximum
 // of the steps BEFORE it (one step of lag) and move that reference only when the running maximum has grown by
@@ -19,9 +20,9 @@
 //
 // What bounds the kernel (profiles/README.md, round 2): the arithmetic of a step -- 128 x (FFMA, MUFU.EX2, FADD),
 // 64 F2FP, 64 FMNMX3 per row -- runs at the MUFU rate (16 ex2 / clk / SM; tools/micro/exp_mix_bench.cu), i.e.
-// 2 x 1 045 clocks per K/V step for the two softmax warps of a scheduler.  The kernel needs about 2 900: the
-// remainder is synchronisation latency (mbarrier waits, TMEM load / store round trips, the unit epilogue) that
-// two warps per scheduler cannot hide from each other.  Measured and NOT helpful: a start offset between the
+// 2 x 1 045 clocks per K/V step for the two softmax warps of a scheduler.  The kernel needs about 2 500 per step
+// plus 1 400 per unit boundary (clock64 trace: -DSFM_ATT_TRACE, tools/att_trace.py): the remainder is per-warp serial
+// latency (first TMEM chunk, P hand-off) that two warps per scheduler cannot fully hide from each other.  Measured and NOT helpful: a start offset between the
 // tiles (any offset random-walks away), strict MUFU turn-taking between the paired warps (their bubbles end up
 // serialised), PRMT instead of F2FP packing, separate issue threads alone.
 #include "tc_common.cuh"
