@@ -317,7 +317,7 @@ def run_ours(a):
             return frames, m_alt.match_frames(frames, names, None)[1]
 
         step_images_alt()
-        n_alt = max(1, min(a.steps, 3))
+        n_alt = max(1, min(a.steps, 5))
         ms_alt, (frames_alt, table_alt) = timed(step_images_alt, n_alt)
         alt = {"value": n_pairs * n_alt / (ms_alt / 1e3), "unit": "pairs/s", "ms_per_step": ms_alt / n_alt,
                "superpoint_precision": other}

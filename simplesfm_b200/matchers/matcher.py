@@ -240,10 +240,7 @@ class Matcher(object):
             # 5 x 49, not 4 x 51 + 41): every launch then fills the SMs equally well, no small tail launch
             runs, plan = plan, []
             for c0, B, k0, k1, h0, h1, groups in runs:
-                n_launch = -(-groups // fuse_limit)
-                base, extra = divmod(groups, n_launch)
-                for li in range(n_launch):
-                    g = base + (1 if li < extra else 0)
+                for g in self.balanced_launches(groups, fuse_limit):
                     nb = min(g * bs, B)
                     plan.append([c0, nb, k0, k1, h0, h1, g])
                     c0 += nb
@@ -313,6 +310,16 @@ class Matcher(object):
     def _shard(self, match_list: np.ndarray) -> np.ndarray:
         lo, hi = self._shard_bounds(len(match_list))
         return match_list[lo:hi]
+
+    @staticmethod
+    def balanced_launches(n_chunks: int, limit: int) -> List[int]:
+        """Chunks per launch for a run of `n_chunks` fusable chunks: the fewest launches the limit allows, of equal
+        size to within one chunk (245 at a limit of 51 -> [49] * 5)."""
+        if n_chunks <= 0:
+            return []
+        n_launch = -(-n_chunks // max(1, limit))
+        base, extra = divmod(n_chunks, n_launch)
+        return [base + (1 if li < extra else 0) for li in range(n_launch)]
 
     @staticmethod
     def pair_list(ids, match_pairs_filter: callable = None) -> np.ndarray:

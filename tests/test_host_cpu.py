@@ -254,3 +254,17 @@ def test_pair_list_matches_itertools_and_vectorised_filters():
     banded.vectorized = True
     got = Matcher.pair_list(ids, banded)
     assert calls == [1] and len(got) == sum(1 for a, b in itertools.combinations(range(40), 2) if b - a < 3)
+
+
+def test_balanced_launches():
+    """Fused chunk runs are cut into the fewest launches the limit allows, equal to within one chunk."""
+    from simplesfm_b200.matchers.matcher import Matcher
+    assert Matcher.balanced_launches(245, 51) == [49] * 5
+    assert Matcher.balanced_launches(245, 32) == [31] * 5 + [30] * 3
+    assert Matcher.balanced_launches(51, 51) == [51] and Matcher.balanced_launches(52, 51) == [26, 26]
+    assert Matcher.balanced_launches(1, 51) == [1] and Matcher.balanced_launches(0, 51) == []
+    for n in range(1, 400):
+        for lim in (1, 7, 51):
+            parts = Matcher.balanced_launches(n, lim)
+            assert sum(parts) == n and max(parts) <= lim and max(parts) - min(parts) <= 1
+            assert len(parts) == -(-n // lim)
