@@ -90,19 +90,31 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap mapIn, const __grid_consta
   const int cblocks = p.Cin / 64;
   const int kblocks = 9 * cblocks;
 
+  // Producer and issuer warps run CONVERGED and one elected lane issues: coordinates, descriptors and barrier
+  // addresses then live in uniform registers.  Under `if (lane == 0)` the compiler wraps every TMA / tcgen05.mma in an
+  // ELECT / R2UR.BROADCAST / branch sequence of ~85 clocks -- more than the 32 (Cout = 64) or 64 (Cout = 128) tensor
+  // clocks of one MMA, which made these kernels issue-bound.
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one_sync();
       int stage = 0, phase = 0;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int img = t / (tiles_y * tiles_x), rem = t % (tiles_y * tiles_x);
         const int y0 = (rem / tiles_x) * 8, x0 = (rem % tiles_x) * 16;
+        int tap = 0, cb = 0;
         for (int kb = 0; kb < kblocks; kb++) {
-          const int tap = kb / cblocks, cb = kb % cblocks;
           mbar_wait(&bars->empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&bars->full[stage], STAGE_BYTES);
           uint8_t* st = sStage + stage * STAGE_BYTES;
-          tma_load_4d(st, &mapIn, &bars->full[stage], cb * 64, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
-          tma_load_2d(st + A_BYTES, &mapW, &bars->full[stage], tap * p.Cin + cb * 64, 0);
+          if (leader) {
+            mbar_arrive_expect_tx(&bars->full[stage], STAGE_BYTES);
+            tma_load_4d(st, &mapIn, &bars->full[stage], cb * 64, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
+            tma_load_2d(st + A_BYTES, &mapW, &bars->full[stage], tap * p.Cin + cb * 64, 0);
+          }
+          __syncwarp();
+          if (++cb == cblocks) {
+            cb = 0;
+            tap++;
+          }
           if (++stage == CONV_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -111,7 +123,8 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap mapIn, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one_sync();
       constexpr uint32_t idesc = umma_idesc_bf16(128, COUT, 0);
       const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sStage), 16, 1024);
       const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sStage + A_BYTES), 16, 1024);
@@ -126,16 +139,20 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap mapIn, const __grid_consta
           tc_fence_after();
           const uint64_t ad = umma_desc_advance(a_desc0, stage * STAGE_BYTES);
           const uint64_t bd = umma_desc_advance(w_desc0, stage * STAGE_BYTES);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4; k++)
-            umma_ss(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, (kb | k) != 0);
-          umma_commit(&bars->empty[stage]);
+            for (int k = 0; k < 4; k++)
+              umma_ss(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, (kb | k) != 0);
+            umma_commit(&bars->empty[stage]);
+          }
+          __syncwarp();
           if (++stage == CONV_STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&bars->acc_full[buf]);
+        if (leader) umma_commit(&bars->acc_full[buf]);
+        __syncwarp();
       }
     }
   } else {
