@@ -207,7 +207,8 @@ SFM_API int sfm_tc_attention(sfm_handle_t h, const void* qkv, long long rows_tot
 
 /* sfm_tc_conv3x3: 3x3 / pad 1 convolution + bias (+ ReLU) as a tcgen05 implicit GEMM (SuperPoint encoder and heads,
  *   superpoint.py:84-99): in [n,H,W,Cin] bf16 NHWC, w [Cout, 9*Cin] bf16 ordered (ky,kx,ci), out [n,H,W,Cout] bf16;
- *   Cin in {64,128}, Cout in {64,128,256}. */
+ *   Cin in {64,128}, Cout in {64,128,256}.  relu: bit 0 = ReLU, bit 1 = fuse the nn.MaxPool2d(2, 2) that follows
+ *   (superpoint.py:114-119) into the epilogue: out is then [n,H/2,W/2,Cout] (H, W even, Cout <= 128). */
 SFM_API int sfm_tc_conv3x3(sfm_handle_t h, const void* in_nhwc, const void* w, const float* bias, void* out_nhwc,
                            int n, int H, int W, int Cin, int Cout, int relu, void* stream);
 

@@ -703,7 +703,7 @@ int sfm_tc_conv3x3(sfm_handle_t h, const void* in_nhwc, const void* w, const flo
   SFM_REQUIRE(h && in_nhwc && w && out_nhwc, "sfm_tc_conv3x3: NULL argument");
   tc::TcConv p;
   p.in = (const __nv_bfloat16*)in_nhwc; p.w = (const __nv_bfloat16*)w; p.bias = bias; p.out = (__nv_bfloat16*)out_nhwc;
-  p.n = n; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.relu = relu;
+  p.n = n; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.relu = relu & 1; p.pool = (relu >> 1) & 1;
   return tc::tc_conv3x3(p, h->sm_count, (cudaStream_t)stream);
 }
 

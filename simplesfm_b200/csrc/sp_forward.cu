@@ -67,10 +67,10 @@ int conv(const SpConv& cv, const float* in, float* out, int n, int H, int W, boo
 // (tc_conv.cu), the two 1x1 head convs on the tcgen05 GEMM with fp32 outputs, so that the exact
 // post-processing chain (softmax, NMS, selection, sampling) is shared with the fp32 path.
 int tconv(sfm_ctx* h, const SpConv& cv, const __nv_bfloat16* in, __nv_bfloat16* out, int n, int H, int W,
-          cudaStream_t st) {
+          cudaStream_t st, bool pool = false) {
   tc::TcConv p;
   p.in = in; p.w = cv.w_h; p.bias = cv.b; p.out = out;
-  p.n = n; p.H = H; p.W = W; p.Cin = cv.cin; p.Cout = cv.cout; p.relu = 1;
+  p.n = n; p.H = H; p.W = W; p.Cin = cv.cin; p.Cout = cv.cout; p.relu = 1; p.pool = pool ? 1 : 0;
   return tc::tc_conv3x3(p, h->sm_count, st);
 }
 
@@ -86,19 +86,18 @@ int head1x1(sfm_ctx* h, const SpConv& cv, const __nv_bfloat16* in, float* out, l
 int detect_bf16(sfm_ctx* h, const float* images, int n, int H, int W, const unsigned char* mask, float thr,
                 int nms_radius, int border, int* cand_counts, const SpBuffers& b, cudaStream_t st) {
   const SpConv* c = h->sp.conv;
+  // the 2 x 2 max-pools run in the epilogues of conv1b / conv2b / conv3b: the full-resolution outputs of those layers
+  // are never written
   SFM_TRY(conv1a_f32(images, c[0].w, c[0].b, nullptr, b.A16, n, H, W, st));
-  SFM_TRY(tconv(h, c[1], b.A16, b.B16, n, H, W, st));
-  SFM_TRY(tc::maxpool2_nhwc_bf16(b.B16, b.A16, n, H, W, 64, st));
-  SFM_TRY(tconv(h, c[2], b.A16, b.B16, n, H / 2, W / 2, st));
-  SFM_TRY(tconv(h, c[3], b.B16, b.A16, n, H / 2, W / 2, st));
-  SFM_TRY(tc::maxpool2_nhwc_bf16(b.A16, b.B16, n, H / 2, W / 2, 64, st));
+  SFM_TRY(tconv(h, c[1], b.A16, b.B16, n, H, W, st, true));
+  SFM_TRY(tconv(h, c[2], b.B16, b.A16, n, H / 2, W / 2, st));
+  SFM_TRY(tconv(h, c[3], b.A16, b.B16, n, H / 2, W / 2, st, true));
   SFM_TRY(tconv(h, c[4], b.B16, b.A16, n, H / 4, W / 4, st));
-  SFM_TRY(tconv(h, c[5], b.A16, b.B16, n, H / 4, W / 4, st));
-  SFM_TRY(tc::maxpool2_nhwc_bf16(b.B16, b.A16, n, H / 4, W / 4, 128, st));
+  SFM_TRY(tconv(h, c[5], b.A16, b.B16, n, H / 4, W / 4, st, true));
   const int hh = H / 8, ww = W / 8;
   const long long cells = (long long)n * hh * ww;
-  SFM_TRY(tconv(h, c[6], b.A16, b.B16, n, hh, ww, st));
-  SFM_TRY(tconv(h, c[7], b.B16, b.feat16, n, hh, ww, st));
+  SFM_TRY(tconv(h, c[6], b.B16, b.A16, n, hh, ww, st));
+  SFM_TRY(tconv(h, c[7], b.A16, b.feat16, n, hh, ww, st));
   SFM_TRY(tconv(h, c[8], b.feat16, b.A16, n, hh, ww, st));                 // convPa
   SFM_TRY(head1x1(h, c[9], b.A16, b.logits, cells, st));                    // convPb -> fp32 logits [cells, 65]
   SFM_TRY(sp_softmax_shuffle(b.logits, 65, b.smap, n, hh, ww, st));

@@ -49,7 +49,24 @@ __device__ __forceinline__ void bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int COUT>
+__device__ __forceinline__ uint4 lds128q(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 max_bf16x8(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162 *pa = reinterpret_cast<const __nv_bfloat162*>(&a), *pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int k = 0; k < 4; k++) pr[k] = __hmax2(pa[k], pb[k]);
+  return r;
+}
+
+// POOL: the 2 x 2 max-pool that follows conv1b / conv2b / conv3b (superpoint.py:114-119) runs in the epilogue -- a
+// tile is 8 x 16 pixels, so every pooling window lies inside it -- and only the pooled map (a quarter of the bytes)
+// is written: the full-resolution activation (157 MB for four 480 x 640 images after conv1b) never reaches HBM.
+template <int COUT, int POOL>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 tc_conv3x3_kernel(const __grid_constant__ CUtensorMap mapIn, const __grid_constant__ CUtensorMap mapW,
                   const __grid_constant__ CUtensorMap mapOut, TcConv p) {
@@ -180,6 +197,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap mapIn, const __grid_consta
           float x = __uint_as_float(r[c & 1][j]) + sBias[c * 32 + j];
           v[j] = p.relu ? fmaxf(x, 0.f) : x;
         }
+        if (!POOL) {
         uint8_t* slab = sO + (slab_i & 1) * SLAB;
         if ((c & 1) == 0) {
           if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // slab used 2 stores ago is free
@@ -202,6 +220,42 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap mapIn, const __grid_consta
           }
           slab_i++;
         }
+        } else {
+        // full-resolution slab (64 channels of the 128 pixels) in sO[0 .. 16 KB), pooled slabs (32 pixels x 128 B,
+        // double-buffered against the TMA store) behind it
+        if ((c & 1) == 0) bar_sync(1, 128);            // the pooling reads of the previous half are done
+        const uint32_t rowa = smem_u32(sO) + pix * 128;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int chunk = (c & 1) * 4 + j;
+          sts128(rowa + ((chunk ^ (pix & 7)) << 4), pack_bf16(v[8 * j], v[8 * j + 1]),
+                 pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
+                 pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        }
+        if ((c & 1) == 1) {
+          if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // pooled slab of 2 stores ago is free
+          bar_sync(1, 128);
+          uint8_t* pslab = sO + SLAB + (slab_i & 1) * 4096;
+          const int pp = etid >> 2, cq = etid & 3;     // pooled pixel (4 rows x 8 columns), 16-channel quarter
+          const int sp = (pp >> 3) * 32 + (pp & 7) * 2;   // top-left source pixel: y = 2 py, x = 2 px, 16 pixels per row
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int chunk = cq * 2 + h;
+            uint4 m = lds128q(smem_u32(sO) + sp * 128 + ((chunk ^ (sp & 7)) << 4));
+            m = max_bf16x8(m, lds128q(smem_u32(sO) + (sp + 1) * 128 + ((chunk ^ ((sp + 1) & 7)) << 4)));
+            m = max_bf16x8(m, lds128q(smem_u32(sO) + (sp + 16) * 128 + ((chunk ^ ((sp + 16) & 7)) << 4)));
+            m = max_bf16x8(m, lds128q(smem_u32(sO) + (sp + 17) * 128 + ((chunk ^ ((sp + 17) & 7)) << 4)));
+            sts128(smem_u32(pslab) + pp * 128 + ((chunk ^ (pp & 7)) << 4), m.x, m.y, m.z, m.w);
+          }
+          fence_proxy_async();
+          bar_sync(1, 128);
+          if (etid == 0) {
+            tma_store_4d(&mapOut, pslab, (c >> 1) * 64, x0 >> 1, y0 >> 1, img);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          slab_i++;
+        }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -218,7 +272,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tmap_nhwc(CUtensorMap* out, const void* base, int n, int H, int W, int C) {
+int make_tmap_nhwc(CUtensorMap* out, const void* base, int n, int H, int W, int C, int box_x = 16, int box_y = 8) {
   static EncodeTiledFn enc = nullptr;
   if (enc == nullptr) {
     void* ptr = nullptr;
@@ -233,7 +287,7 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, int n, int H, int W, int 
   }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, 16, 8, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_x, (cuuint32_t)box_y, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -245,18 +299,19 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, int n, int H, int W, int 
   return SFM_OK;
 }
 
-template <int COUT>
+template <int COUT, int POOL>
 int launch_conv(const TcConv& p, int num_sms, cudaStream_t st) {
   CUtensorMap mIn, mW, mOut;
   SFM_TRY(make_tmap_nhwc(&mIn, p.in, p.n, p.H, p.W, p.Cin));
-  SFM_TRY(make_tmap_nhwc(&mOut, p.out, p.n, p.H, p.W, COUT));
+  if (POOL) SFM_TRY(make_tmap_nhwc(&mOut, p.out, p.n, p.H / 2, p.W / 2, COUT, 8, 4));
+  else SFM_TRY(make_tmap_nhwc(&mOut, p.out, p.n, p.H, p.W, COUT));
   SFM_TRY(make_tmap_bf16(&mW, p.w, COUT, 9ull * p.Cin, 9ull * p.Cin, COUT));
   const int tiles = p.n * cdiv(p.H, 8) * cdiv(p.W, 16);
   const size_t smem = (size_t)CONV_STAGES * (A_BYTES + COUT * 128) + 2 * SLAB + COUT * sizeof(float) + sizeof(ConvBars) +
                       1024;
-  SFM_SMEM_OPT_IN(tc_conv3x3_kernel<COUT>, smem);
+  SFM_SMEM_OPT_IN((tc_conv3x3_kernel<COUT, POOL>), smem);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  tc_conv3x3_kernel<COUT><<<grid, CONV_THREADS, smem, st>>>(mIn, mW, mOut, p);
+  tc_conv3x3_kernel<COUT, POOL><<<grid, CONV_THREADS, smem, st>>>(mIn, mW, mOut, p);
   SFM_LAUNCH_CHECK();
   return SFM_OK;
 }
@@ -289,10 +344,11 @@ __global__ void maxpool2_bf16_kernel(const uint4* __restrict__ in, uint4* __rest
 int tc_conv3x3(const TcConv& p, int num_sms, cudaStream_t st) {
   SFM_REQUIRE(p.Cin == 64 || p.Cin == 128, "tc_conv3x3: Cin must be 64 or 128 (got %d)", p.Cin);
   SFM_REQUIRE(p.n > 0 && p.H > 0 && p.W > 0, "tc_conv3x3: bad image dims");
+  SFM_REQUIRE(!p.pool || (p.H % 2 == 0 && p.W % 2 == 0 && p.Cout <= 128), "tc_conv3x3: pooled output needs even H, W and Cout <= 128");
   switch (p.Cout) {
-    case 64: return launch_conv<64>(p, num_sms, st);
-    case 128: return launch_conv<128>(p, num_sms, st);
-    case 256: return launch_conv<256>(p, num_sms, st);
+    case 64: return p.pool ? launch_conv<64, 1>(p, num_sms, st) : launch_conv<64, 0>(p, num_sms, st);
+    case 128: return p.pool ? launch_conv<128, 1>(p, num_sms, st) : launch_conv<128, 0>(p, num_sms, st);
+    case 256: return launch_conv<256, 0>(p, num_sms, st);
     default: set_error("tc_conv3x3: Cout must be 64, 128 or 256 (got %d)", p.Cout); return SFM_ERR_UNSUPPORTED;
   }
 }

@@ -92,8 +92,9 @@ struct TcConv {
   const __nv_bfloat16* in = nullptr;  // [n, H, W, Cin]
   const __nv_bfloat16* w = nullptr;   // [Cout, 9 * Cin]  (tap-major, channel-minor)
   const float* bias = nullptr;
-  __nv_bfloat16* out = nullptr;       // [n, H, W, Cout]
+  __nv_bfloat16* out = nullptr;       // [n, H, W, Cout]; with pool: [n, H / 2, W / 2, Cout]
   int n = 0, H = 0, W = 0, Cin = 0, Cout = 0, relu = 1;
+  int pool = 0;                       // fuse nn.MaxPool2d(2, 2) into the epilogue (H, W even): only the pooled map is written
 };
 int tc_conv3x3(const TcConv& p, int num_sms, cudaStream_t st);
 int maxpool2_nhwc_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int n, int H, int W, int C, cudaStream_t st);

@@ -276,6 +276,31 @@ def test_tc_conv3x3(handle, dev, n, H, W, Cin, Cout):
     torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("n,H,W,Cin,Cout", [(2, 48, 64, 64, 64), (1, 40, 72, 64, 128), (3, 24, 48, 128, 128)])
+def test_tc_conv3x3_fused_maxpool(handle, dev, n, H, W, Cin, Cout):
+    """The 2 x 2 max-pool fused into the convolution epilogue (only the pooled map is written) equals
+    max_pool2d(relu(conv2d)) of the UNFUSED kernel bit for bit, and torch within bf16 noise; 40 x 72 has partial
+    tiles in both directions."""
+    from simplesfm_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(H * W + Cin + 1)
+    x = torch.randn(n, Cin, H, W, generator=g).to(dev).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).to(dev).bfloat16()
+    bias = torch.randn(Cout, generator=g).to(dev)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    w_k = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    full = torch.zeros(n, H, W, Cout, dtype=torch.bfloat16, device=dev)
+    pooled = torch.full((n, H // 2, W // 2, Cout), -7.0, dtype=torch.bfloat16, device=dev)
+    L = _lib.lib()
+    _lib.check(L.sfm_tc_conv3x3(handle.h, x_nhwc.data_ptr(), w_k.data_ptr(), bias.data_ptr(), full.data_ptr(),
+                                n, H, W, Cin, Cout, 1, _stream()))
+    _lib.check(L.sfm_tc_conv3x3(handle.h, x_nhwc.data_ptr(), w_k.data_ptr(), bias.data_ptr(), pooled.data_ptr(),
+                                n, H, W, Cin, Cout, 3, _stream()))
+    want = torch.nn.functional.max_pool2d(full.permute(0, 3, 1, 2).float(), 2, 2).permute(0, 2, 3, 1)
+    assert torch.equal(pooled.float(), want)
+    ref = torch.nn.functional.max_pool2d(torch.relu(torch.nn.functional.conv2d(x.float(), w.float(), bias, padding=1)), 2, 2)
+    torch.testing.assert_close(pooled.float(), ref.permute(0, 2, 3, 1), rtol=2e-2, atol=2e-2)
+
+
 def test_superpoint_bf16_vs_fp32(sp_weights, dev):
     """SuperPoint with tcgen05 convolutions (bf16) against the exact fp32 path: dense maps within bf16
     noise, and the detected keypoint sets overlap (stated-precision mode; keypoints are not bit-exact)."""
