@@ -268,3 +268,35 @@ def test_balanced_launches():
             parts = Matcher.balanced_launches(n, lim)
             assert sum(parts) == n and max(parts) <= lim and max(parts) - min(parts) <= 1
             assert len(parts) == -(-n // lim)
+
+
+def test_compact_tables_to_dict_views_and_empties():
+    """CompactTables.to_dict: pair order, np.int64 keys like the reference's table, zero-length tables, empty set."""
+    import numpy as np
+    from simplesfm_b200.distributed import CompactTables, concat_tables
+    pairs = np.array([[1, 2], [1, 3], [2, 3]], np.int64)
+    lens = np.array([2, 0, 3], np.int64)
+    rows = np.arange(10, dtype=np.uint32).reshape(5, 2)
+    d = CompactTables(pairs, lens, rows).to_dict()
+    assert list(d.keys()) == [(1, 2), (1, 3), (2, 3)] and all(isinstance(k[0], np.int64) for k in d)
+    assert d[(1, 2)].tolist() == [[0, 1], [2, 3]] and d[(1, 3)].shape == (0, 2) and d[(2, 3)].tolist() == [[4, 5], [6, 7], [8, 9]]
+    assert d[(2, 3)].dtype == np.uint32 and np.shares_memory(d[(2, 3)], rows)
+    assert concat_tables([]).to_dict() == {}
+    both = concat_tables([CompactTables(pairs[:1], lens[:1], rows[:2]), CompactTables(pairs[1:], lens[1:], rows[2:])])
+    assert {k: v.tolist() for k, v in both.to_dict().items()} == {k: v.tolist() for k, v in d.items()}
+
+
+def test_sparse_depth_entries_edge_cases():
+    """camera_point_entries: image ids outside the camera set are ignored, nothing selected -> empty arrays,
+    a point observed twice by the same camera counts once."""
+    import numpy as np
+    from simplesfm_b200.dataset import simple_sfm_dataset_utils as U
+    err = np.array([0.5, 0.5, 5.0])
+    tp = np.array([0, 0, 0, 1, 2, 2])
+    ti = np.array([1, 1, 9, 2, 1, 2])
+    cam, pt = U.camera_point_entries(err, tp, ti, [0, 1], 2.0)
+    assert cam.tolist() == [0, 1] and pt.tolist() == [0, 1]          # point 2 fails the error test, image 9 is unknown
+    cam, pt = U.camera_point_entries(err, tp, ti, [5, 6], 2.0)
+    assert len(cam) == 0 and len(pt) == 0
+    cam, pt = U.camera_point_entries(np.zeros(0), np.zeros(0, np.int64), np.zeros(0, np.int64), [0], 2.0)
+    assert len(cam) == 0
